@@ -1,0 +1,78 @@
+/* zstdmt_b200_dev.h — device-resident batch entry points of libzstdmt_b200.so.
+ *
+ * These are what the host pipeline behind LZ4MT_* / ZSTDCB_* calls per batch, exported so a
+ * caller that already holds its data in HBM (bench.py's device-timed metric, a GPU-side
+ * producer) can skip the host staging.  Plain C ABI: device pointers + sizes + a CUDA stream
+ * handle passed as void*.  All work is enqueued on `stream`; nothing synchronises.
+ *
+ * What each call replaces in the reference (one call = the codec step of every worker
+ * iteration of a whole batch of chunks):
+ *   zmt_lz4_compress_device    LZ4F_compressFrame + 12-byte header, lib/lz4-mt_compress.c:280-298
+ *   zmt_lz4_decompress_device  LZ4F_decompress, lib/lz4-mt_decompress.c:328-362
+ *   zmt_zstd_compress_device   ZSTD_compress + 12-byte header, lib/zstd-mt_compress.c:284-302
+ *   zmt_zstd_decompress_device ZSTD_decompressStream loop, lib/zstd-mt_decompress.c:442-527
+ */
+#ifndef ZSTDMT_B200_DEV_H
+#define ZSTDMT_B200_DEV_H
+#include <stddef.h>
+#include <stdint.h>
+
+#define ZMT_LZ4_TMP_STRIDE 65824u     /* >= LZ4 worst case for a 64 KiB block (65536 + 257 + 16), 16-byte multiple */
+
+/* per-frame / per-call status codes */
+#define ZMT_ST_OK               0u
+#define ZMT_ST_TRUNCATED        1u
+#define ZMT_ST_BAD_MAGIC        2u
+#define ZMT_ST_BAD_HEADER       3u
+#define ZMT_ST_HDR_CHECKSUM     4u
+#define ZMT_ST_BLOCK            5u
+#define ZMT_ST_DST_SMALL        6u
+#define ZMT_ST_CONTENT_CHECKSUM 7u
+#define ZMT_ST_CONTENT_SIZE     8u
+#define ZMT_ST_TRAILING         9u
+#define ZMT_ST_UNSUPPORTED      10u
+#define ZMT_ST_CUDA             11u
+#define ZMT_ST_BAD_ARG          12u
+#define ZMT_ST_HAS_CHK          0x100u   /* internal flag between decode and verify kernels */
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* number of chunks (= frames) an input of in_bytes cut every chunk_size bytes produces;
+ * an empty input still yields one frame (lib/lz4-mt_compress.c:265) */
+uint32_t zmt_chunk_count(uint64_t in_bytes, uint32_t chunk_size);
+
+/* ---- LZ4 ----
+ * Input layout: chunk c starts at d_in + c*chunk_size.  Its length is d_chunk_bytes[c] when
+ * that (device) array is given, else derived from in_bytes (all full, last one short).
+ * Output: the framed stream, frames back to back; d_frame_off[c] = offset of frame c's
+ * 12-byte skippable header, d_frame_off[nchunks] = total bytes. */
+size_t   zmt_lz4c_workspace_bytes(uint32_t nchunks, uint32_t chunk_size);
+uint64_t zmt_lz4c_out_bound(uint32_t nchunks, uint32_t chunk_size);
+int      zmt_lz4_compress_device(const void* d_in, uint64_t in_bytes, uint32_t chunk_size, const uint32_t* d_chunk_bytes,
+                                 uint32_t nchunks, void* d_work, void* d_out, uint64_t* d_frame_off, void* stream);
+
+/* d_frame_off[f] = offset (in d_in) of frame f's 12-byte header, d_frame_csize[f] = its payload
+ * size; d_out_off[f..f+1] = where frame f's content goes and how much room it has;
+ * d_out_size[f] / d_status[f] receive decoded bytes and a ZMT_ST_* code. */
+size_t   zmt_lz4d_workspace_bytes(uint32_t nframes);
+int      zmt_lz4_decompress_device(const void* d_in, const uint64_t* d_frame_off, const uint32_t* d_frame_csize, uint32_t nframes,
+                                   void* d_out, const uint64_t* d_out_off, uint64_t* d_out_size, uint32_t* d_status,
+                                   void* d_work, void* stream);
+
+/* ---- synthetic inputs (csrc/datagen.c) ---- */
+void zmt_gen_chunk(int kind, uint64_t chunk_index, uint8_t* buf, size_t n);
+void zmt_gen_stream(int kind, uint64_t first, uint64_t stride, size_t chunk, uint8_t* buf, size_t total, int nthreads);
+
+/* ---- memory-to-memory drivers of the callback API (csrc/memio_glue.c) ----
+ * stats[0..4] = bytes written, frames, Insize counter, Outsize counter, (reads<<32 | writes) */
+size_t zmt_lz4_compress_mem(int threads, int level, int chunk, const void* src, size_t n, void* dst, size_t cap, size_t* stats);
+size_t zmt_lz4_decompress_mem(int threads, int inputsize, const void* src, size_t n, void* dst, size_t cap, size_t* stats);
+size_t zmt_zstd_compress_mem(int threads, int level, int chunk, const void* src, size_t n, void* dst, size_t cap, size_t* stats);
+size_t zmt_zstd_decompress_mem(int threads, int inputsize, const void* src, size_t n, void* dst, size_t cap, size_t* stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,88 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads and exports every symbol the
+headers in include/ declare; argument validation and error plumbing behave like the
+reference (no compute calls — those need a GPU)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+import zstdmt_b200 as z
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    names = set()
+    for h in ("zstdmt_b200_lz4.h", "zstdmt_b200_zstd.h", "zstdmt_b200_dev.h"):
+        p = os.path.join(ROOT, "include", h)
+        if not os.path.exists(p):
+            continue
+        txt = open(p).read()
+        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        for m in re.finditer(r"\b((?:LZ4MT|ZSTDCB|ZSTDMT|zmt)_\w+)\s*\(", txt):
+            names.add(m.group(1))
+    names.discard("ZSTDCB_PREFIX"); names.discard("ZSTDCB_ERROR")
+    return sorted(names)
+
+
+def test_library_exports_every_declared_symbol():
+    L = z.lib()
+    syms = declared_symbols()
+    assert len(syms) >= 44
+    for s in syms:
+        assert hasattr(L, s), "missing export: " + s
+    out = subprocess.run(["nm", "-D", z.LIB_PATH], capture_output=True, text=True).stdout
+    assert " B lz4mt_errcode" in out or " D lz4mt_errcode" in out
+    assert " B zstdmt_errcode" in out or " D zstdmt_errcode" in out
+
+
+def test_create_validates_like_reference():
+    L = z.lib()
+    # lz4-mt_compress.c:103-108 / lz4-mt_decompress.c:101-102
+    assert not L.LZ4MT_createCCtx(0, 1, 0) and not L.LZ4MT_createCCtx(129, 1, 0)
+    assert not L.LZ4MT_createCCtx(1, 0, 0) and not L.LZ4MT_createCCtx(1, 13, 0)
+    assert not L.LZ4MT_createDCtx(0, 0) and not L.LZ4MT_createDCtx(129, 0)
+    # zstd-mt_compress.c:105-110
+    assert not L.ZSTDCB_createCCtx(0, 3, 0) and not L.ZSTDCB_createCCtx(1, 23, 0) and not L.ZSTDCB_createCCtx(1, 0, 0)
+    c = L.LZ4MT_createCCtx(4, 1, 1 << 20); assert c
+    assert L.LZ4MT_GetFramesCCtx(c) == 0 and L.LZ4MT_GetInsizeCCtx(c) == 0 and L.LZ4MT_GetOutsizeCCtx(c) == 0
+    L.LZ4MT_freeCCtx(c); L.LZ4MT_freeCCtx(None)
+    d = L.ZSTDMT_createDCtx(2, 0); assert d
+    L.ZSTDMT_freeDCtx(d)
+
+
+def test_error_convention():
+    L = z.lib()
+    size_t_max = ctypes.c_size_t(-1).value
+    # isError(c) <=> c > (size_t)-maxCode   (lz4 maxCode 10, zstd 11)
+    assert L.LZ4MT_isError(size_t_max - 8 + 1)      # (size_t)-8 compression_library
+    assert not L.LZ4MT_isError(0) and not L.LZ4MT_isError(size_t_max - 10 + 1)
+    assert L.ZSTDCB_isError(size_t_max - 10 + 1) and not L.ZSTDCB_isError(size_t_max - 11 + 1)
+    assert L.LZ4MT_getErrorString(size_t_max - 4 + 1) == b"Malformed input"
+    assert L.ZSTDCB_getErrorString(size_t_max - 5 + 1) == b"Malformed input"
+    assert L.LZ4MT_getErrorString(size_t_max - 9 + 1) == b"Unspecified lz4mt error code"   # canceled has no entry (lz4-mt_common.c:40-62)
+    # NULL contexts: lz4 -> compressionParameter_unsupported (lz4-mt_compress.c:317), zstd -> init_missing (zstd-mt_compress.c:327)
+    assert L.LZ4MT_compressCCtx(None, None) == size_t_max - 7 + 1
+    assert L.ZSTDCB_compressCCtx(None, None) == size_t_max - 2 + 1
+    assert L.LZ4MT_GetInsizeCCtx(None) == 0
+    assert L.ZSTDCB_GetInsizeCCtx(None) == size_t_max - 2 + 1
+
+
+def test_no_gpu_fails_loudly():
+    """Without a CUDA device the product must return an error — never fall back to a CPU codec."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import numpy as np
+    rc, out, st = z.compress_mem(z.CODEC_LZ4, np.zeros(1000, np.uint8), chunk=1 << 16)
+    assert z.lib().LZ4MT_isError(rc) and out.size == 0
+
+
+def test_chunk_count_and_bounds():
+    L = z.lib()
+    assert L.zmt_chunk_count(0, 1 << 20) == 1            # empty input still yields one frame (lz4-mt_compress.c:265)
+    assert L.zmt_chunk_count(1, 1 << 20) == 1
+    assert L.zmt_chunk_count((1 << 20) + 1, 1 << 20) == 2
+    assert L.zmt_lz4c_out_bound(1, 1 << 20) >= 1048679   # LZ4F_compressFrameBound(1 MiB)+12 (Appendix A)

@@ -1,0 +1,190 @@
+"""zstdmt_b200 — B200-native replacement for zstdmt's per-chunk LZ4 / Zstandard hot path.
+
+The product is the C-ABI shared library ``libzstdmt_b200.so`` (CUDA kernels for sm_100a +
+host pipeline exporting LZ4MT_* / ZSTDCB_* / ZSTDMT_*, see include/).  This module is only
+the thin ctypes binding used by tests and bench.py; it never computes anything itself and it
+raises if the native library is missing (no Python / CPU fallback).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libzstdmt_b200.so")
+
+c_sz = ctypes.c_size_t
+c_u64 = ctypes.c_uint64
+c_u32 = ctypes.c_uint32
+c_vp = ctypes.c_void_p
+
+CODEC_LZ4, CODEC_ZSTD = 1, 2
+GEN_ZEROS, GEN_TEXT, GEN_MIX, GEN_RANDOM = 0, 1, 2, 3
+
+ST_NAMES = {0: "ok", 1: "truncated", 2: "bad_magic", 3: "bad_header", 4: "hdr_checksum", 5: "block", 6: "dst_small",
+            7: "content_checksum", 8: "content_size", 9: "trailing", 10: "unsupported", 11: "cuda", 12: "bad_arg"}
+
+_lib = None
+
+
+class Buffer(ctypes.Structure):
+    """LZ4MT_Buffer / ZSTDCB_Buffer (include/zstdmt_b200_lz4.h)."""
+    _fields_ = [("buf", c_vp), ("size", c_sz), ("allocated", c_sz)]
+
+
+RW_FN = ctypes.CFUNCTYPE(ctypes.c_int, c_vp, ctypes.POINTER(Buffer))
+
+
+class RdWr(ctypes.Structure):
+    """LZ4MT_RdWr_t / ZSTDCB_RdWr_t."""
+    _fields_ = [("fn_read", RW_FN), ("arg_read", c_vp), ("fn_write", RW_FN), ("arg_write", c_vp)]
+
+
+def lib():
+    """Load libzstdmt_b200.so (building it with nvcc if the .so is absent)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _b
+        _b.build_product()
+    L = ctypes.CDLL(LIB_PATH)
+    for name in ("lz4_compress_mem", "zstd_compress_mem"):
+        f = getattr(L, "zmt_" + name); f.restype = c_sz
+        f.argtypes = [ctypes.c_int] * 3 + [c_vp, c_sz, c_vp, c_sz, ctypes.POINTER(c_sz)]
+    for name in ("lz4_decompress_mem", "zstd_decompress_mem"):
+        f = getattr(L, "zmt_" + name); f.restype = c_sz
+        f.argtypes = [ctypes.c_int] * 2 + [c_vp, c_sz, c_vp, c_sz, ctypes.POINTER(c_sz)]
+    L.zmt_gen_stream.restype = None
+    L.zmt_gen_stream.argtypes = [ctypes.c_int, c_u64, c_u64, c_sz, c_vp, c_sz, ctypes.c_int]
+    L.zmt_chunk_count.restype = c_u32; L.zmt_chunk_count.argtypes = [c_u64, c_u32]
+    L.zmt_lz4c_workspace_bytes.restype = c_sz; L.zmt_lz4c_workspace_bytes.argtypes = [c_u32, c_u32]
+    L.zmt_lz4c_out_bound.restype = c_u64; L.zmt_lz4c_out_bound.argtypes = [c_u32, c_u32]
+    L.zmt_lz4_compress_device.restype = ctypes.c_int
+    L.zmt_lz4_compress_device.argtypes = [c_vp, c_u64, c_u32, c_vp, c_u32, c_vp, c_vp, c_vp, c_vp]
+    L.zmt_lz4d_workspace_bytes.restype = c_sz; L.zmt_lz4d_workspace_bytes.argtypes = [c_u32]
+    L.zmt_lz4_decompress_device.restype = ctypes.c_int
+    L.zmt_lz4_decompress_device.argtypes = [c_vp, c_vp, c_vp, c_u32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
+    for pre, api in (("LZ4MT", "lz4"), ("ZSTDCB", "zstd"), ("ZSTDMT", "zstd")):
+        getattr(L, pre + "_createCCtx").restype = c_vp; getattr(L, pre + "_createCCtx").argtypes = [ctypes.c_int] * 3
+        getattr(L, pre + "_createDCtx").restype = c_vp; getattr(L, pre + "_createDCtx").argtypes = [ctypes.c_int] * 2
+        for k in ("compressCCtx", "decompressDCtx"):
+            f = getattr(L, pre + "_" + k); f.restype = c_sz; f.argtypes = [c_vp, ctypes.POINTER(RdWr)]
+        for k in ("GetFramesCCtx", "GetInsizeCCtx", "GetOutsizeCCtx", "GetFramesDCtx", "GetInsizeDCtx", "GetOutsizeDCtx"):
+            f = getattr(L, pre + "_" + k); f.restype = c_sz; f.argtypes = [c_vp]
+        for k in ("freeCCtx", "freeDCtx"):
+            f = getattr(L, pre + "_" + k); f.restype = None; f.argtypes = [c_vp]
+        getattr(L, pre + "_isError").restype = ctypes.c_uint; getattr(L, pre + "_isError").argtypes = [c_sz]
+        getattr(L, pre + "_getErrorString").restype = ctypes.c_char_p; getattr(L, pre + "_getErrorString").argtypes = [c_sz]
+    _lib = L
+    return L
+
+
+# ------------------------------------------------------------------ synthetic inputs
+def gen_stream(kind, nbytes, chunk, first=0, stride=1, threads=None, out=None):
+    """Deterministic synthetic stream (csrc/datagen.c).  Returns a numpy uint8 array."""
+    if out is None:
+        out = np.empty(nbytes, dtype=np.uint8)
+    if threads is None:
+        threads = min(32, os.cpu_count() or 1)
+    if nbytes:
+        lib().zmt_gen_stream(kind, first, stride, chunk, out.ctypes.data, nbytes, threads)
+    return out
+
+
+# ------------------------------------------------------------------ memory-to-memory driver of the callback API
+def _mem_call(fn, ints, data, cap):
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    out = np.empty(cap, dtype=np.uint8)
+    st = (c_sz * 5)()
+    rc = fn(*ints, data.ctypes.data, data.size, out.ctypes.data, cap, st)
+    return rc, out[: st[0]], {"out_bytes": st[0], "frames": st[1], "insize": st[2], "outsize": st[3],
+                              "reads": st[4] >> 32, "writes": st[4] & 0xFFFFFFFF}
+
+
+def mt_bound(n, chunk):
+    nch = max(1, -(-n // chunk))
+    return n + n // 128 + nch * (64 + 4 * (chunk // 65536 + 1)) + 4096
+
+
+def compress_mem(codec, data, threads=4, level=1, chunk=1 << 20):
+    """{LZ4MT,ZSTDCB}_compressCCtx through in-memory callbacks (csrc/memio_glue.c)."""
+    L = lib()
+    fn = L.zmt_lz4_compress_mem if codec == CODEC_LZ4 else L.zmt_zstd_compress_mem
+    return _mem_call(fn, (threads, level, chunk), data, mt_bound(len(data), chunk))
+
+
+def decompress_mem(codec, data, out_cap, threads=4, inputsize=0):
+    L = lib()
+    fn = L.zmt_lz4_decompress_mem if codec == CODEC_LZ4 else L.zmt_zstd_decompress_mem
+    return _mem_call(fn, (threads, inputsize), data, out_cap)
+
+
+# ------------------------------------------------------------------ device-resident batch API (torch only as allocator / stream owner)
+def _torch():
+    import torch
+    return torch
+
+
+def scan_frames(framed):
+    """Walk a framed stream on the host: offsets of the 12-byte headers, payload sizes."""
+    b = np.ascontiguousarray(framed, dtype=np.uint8)
+    offs, sizes, pos, n = [], [], 0, b.size
+    while pos < n:
+        if n - pos < 12:
+            raise ValueError("truncated skippable header")
+        magic, four, cs = np.frombuffer(b[pos:pos + 12].tobytes(), dtype="<u4")
+        if magic != 0x184D2A50 or four != 4:
+            raise ValueError("bad skippable header at %d" % pos)
+        offs.append(pos); sizes.append(int(cs)); pos += 12 + int(cs)
+    if pos != n:
+        raise ValueError("truncated payload")
+    return np.array(offs, dtype=np.uint64), np.array(sizes, dtype=np.uint32)
+
+
+class Lz4DeviceCompressor:
+    """Pre-allocated device buffers + one call per batch: zmt_lz4_compress_device."""
+
+    def __init__(self, in_bytes, chunk, device="cuda"):
+        torch = _torch(); L = lib()
+        self.chunk, self.in_bytes = chunk, in_bytes
+        self.nchunks = L.zmt_chunk_count(in_bytes, chunk)
+        self.work = torch.empty(L.zmt_lz4c_workspace_bytes(self.nchunks, chunk), dtype=torch.uint8, device=device)
+        self.out = torch.empty(L.zmt_lz4c_out_bound(self.nchunks, chunk), dtype=torch.uint8, device=device)
+        self.frame_off = torch.zeros(self.nchunks + 1, dtype=torch.int64, device=device)
+
+    def run(self, d_in, stream=None):
+        torch = _torch()
+        s = stream if stream is not None else torch.cuda.current_stream()
+        rc = lib().zmt_lz4_compress_device(d_in.data_ptr(), self.in_bytes, self.chunk, None, self.nchunks,
+                                           self.work.data_ptr(), self.out.data_ptr(), self.frame_off.data_ptr(), s.cuda_stream)
+        if rc != 0:
+            raise RuntimeError("zmt_lz4_compress_device failed: %s" % ST_NAMES.get(rc, rc))
+        return self.out, self.frame_off
+
+
+class Lz4DeviceDecompressor:
+    """zmt_lz4_decompress_device over a device-resident framed stream."""
+
+    def __init__(self, frame_off, frame_csize, out_sizes, device="cuda"):
+        torch = _torch(); L = lib()
+        self.n = len(frame_off)
+        self.d_off = torch.from_numpy(np.asarray(frame_off, dtype=np.int64)).to(device)
+        self.d_cs = torch.from_numpy(np.asarray(frame_csize, dtype=np.int32)).to(device)
+        oo = np.zeros(self.n + 1, dtype=np.int64); oo[1:] = np.cumsum(np.asarray(out_sizes, dtype=np.int64))
+        self.out_total = int(oo[-1])
+        self.d_out_off = torch.from_numpy(oo).to(device)
+        self.out = torch.empty(max(self.out_total, 1), dtype=torch.uint8, device=device)
+        self.out_size = torch.zeros(self.n, dtype=torch.int64, device=device)
+        self.status = torch.zeros(self.n, dtype=torch.int32, device=device)
+        self.work = torch.empty(L.zmt_lz4d_workspace_bytes(self.n), dtype=torch.uint8, device=device)
+
+    def run(self, d_framed, stream=None):
+        torch = _torch()
+        s = stream if stream is not None else torch.cuda.current_stream()
+        rc = lib().zmt_lz4_decompress_device(d_framed.data_ptr(), self.d_off.data_ptr(), self.d_cs.data_ptr(), self.n,
+                                             self.out.data_ptr(), self.d_out_off.data_ptr(), self.out_size.data_ptr(),
+                                             self.status.data_ptr(), self.work.data_ptr(), s.cuda_stream)
+        if rc != 0:
+            raise RuntimeError("zmt_lz4_decompress_device failed: %s" % ST_NAMES.get(rc, rc))
+        return self.out, self.status

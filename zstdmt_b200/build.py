@@ -1,0 +1,68 @@
+"""Build the in-tree native libraries (no torch extension machinery, plain nvcc / gcc).
+
+  zstdmt_b200/libzstdmt_b200.so   CUDA kernels (sm_100a) + host pipeline + C-ABI   [the product]
+  oracle/liboracle.so             CPU restatement                                  [test infrastructure]
+  oracle/_ref/libzstdmt_ref.so    unmodified reference wrapper, only when /root/reference exists
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libzstdmt_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC,-O3,-pthread", "-DGLUE_PREFIX=zmt_", "-shared",
+]
+
+
+def _sources():
+    srcs = []
+    for f in sorted(os.listdir(CSRC)):
+        if f.endswith((".cu", ".cpp", ".c")):
+            srcs.append(os.path.join(CSRC, f))
+    return srcs
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_product(force=False, verbose=False):
+    srcs = _sources()
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    if not force and not _stale(LIB, deps):
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    if not os.path.exists(nvcc):
+        nvcc = "nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs + ["-lpthread"]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed building libzstdmt_b200.so")
+    return LIB
+
+
+def build_oracle():
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("oracle build failed")
+
+
+def build_all(force=False, verbose=False):
+    build_product(force=force, verbose=verbose)
+    build_oracle()
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print("ok:", LIB)

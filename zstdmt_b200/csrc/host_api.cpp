@@ -1,0 +1,743 @@
+// host_api.cpp — the drop-in boundary: LZ4MT_* / ZSTDCB_* (+ ZSTDMT_* aliases) on top of the CUDA kernels.
+//
+// Replaces the pthread worker pools of
+//   /root/reference/lib/lz4-mt_compress.c:207-353   (pt_compress, pt_write, LZ4MT_compressCCtx)
+//   /root/reference/lib/lz4-mt_decompress.c:165-567 (pt_read, pt_decompress, pt_write, LZ4MT_decompressDCtx)
+//   /root/reference/lib/zstd-mt_compress.c:177-392  and  lib/zstd-mt_decompress.c:209-843
+// with one software pipeline per call:
+//
+//   reader thread  : fn_read -> pinned staging slot (B chunks / frames per slot)
+//   submit (caller): H2D -> kernels -> D2H of the size table, one CUDA stream per slot,
+//                    slots dealt round-robin over the GPUs named by ZSTDMT_GPUS
+//   writer thread  : waits for the slot's event, D2H of the used bytes, fn_write strictly in
+//                    frame order (the pt_write rule, lz4-mt_compress.c:186-202)
+//
+// Callback contract kept: reads never overlap reads, writes never overlap writes, a read and a
+// write may overlap (as with the reference's read_mutex / write_mutex).  No CPU codec fallback:
+// if the CUDA runtime or a kernel fails the call returns *_error_compression_library.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
+#include "zmt_dev.h"
+
+extern "C" {
+size_t   zmt_zstdc_workspace_bytes(uint32_t nchunks, uint32_t chunk_size) __attribute__((weak));
+uint64_t zmt_zstdc_out_bound(uint32_t nchunks, uint32_t chunk_size) __attribute__((weak));
+int      zmt_zstd_compress_device(const void*, uint64_t, uint32_t, const uint32_t*, uint32_t, void*, void*, uint64_t*, void*) __attribute__((weak));
+size_t   zmt_zstdd_workspace_bytes(uint32_t nframes) __attribute__((weak));
+int      zmt_zstd_decompress_device(const void*, const uint64_t*, const uint32_t*, uint32_t, void*, const uint64_t*, uint64_t*, uint32_t*, void*, void*) __attribute__((weak));
+}
+
+namespace {
+
+// ------------------------------------------------------------------ generic boundary types
+struct GenBuffer { void* buf; size_t size; size_t allocated; };     // == LZ4MT_Buffer == ZSTDCB_Buffer
+typedef int (gen_rw_fn)(void* arg, GenBuffer* b);
+struct GenRdWr { gen_rw_fn* fn_read; void* arg_read; gen_rw_fn* fn_write; void* arg_write; };
+
+enum { CODEC_LZ4 = 1, CODEC_ZSTD = 2 };
+#define MT_MAGIC_SKIPPABLE 0x184D2A50u
+#define LZ4F_MAGIC         0x184D2204u
+#define ZSTD_MAGIC         0xFD2FB528u
+
+// error numbering differs between the codecs (lz4-mt.h:41-53 vs zstd-mt.h:41-54)
+struct ErrCodes { size_t mem, read_fail, write_fail, data_error, frame_compress, frame_decompress, param, library, canceled, init_missing; };
+const ErrCodes kErrLz4  = { (size_t)-1, (size_t)-2, (size_t)-3, (size_t)-4, (size_t)-5, (size_t)-6, (size_t)-7, (size_t)-8, (size_t)-9, (size_t)-7 };
+const ErrCodes kErrZstd = { (size_t)-1, (size_t)-3, (size_t)-4, (size_t)-5, (size_t)-6, (size_t)-7, (size_t)-8, (size_t)-9, (size_t)-10, (size_t)-2 };
+
+inline uint32_t rd32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+inline uint64_t rd64(const uint8_t* p) { return (uint64_t)rd32(p) | ((uint64_t)rd32(p + 4) << 32); }
+
+// callback return -> library error (mt_error, lz4-mt_compress.c:161-173: write failures also map to read_fail)
+inline size_t mt_error(const ErrCodes& E, int rv)
+{
+    switch (rv) { case -1: return E.read_fail; case -2: return E.canceled; case -3: return E.mem; }
+    return E.read_fail;
+}
+
+size_t env_size(const char* name, size_t dflt)
+{
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    char* end = nullptr; unsigned long long x = strtoull(v, &end, 10);
+    return (end && end != v) ? (size_t)x : dflt;
+}
+
+std::vector<int> env_devices()
+{
+    std::vector<int> devs;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return devs;
+    const char* v = getenv("ZSTDMT_GPUS");
+    if (v && *v) {
+        if (!strcmp(v, "all")) { for (int i = 0; i < ndev; i++) devs.push_back(i); return devs; }
+        const char* p = v;
+        while (*p) {
+            char* end = nullptr; long d = strtol(p, &end, 10);
+            if (end == p) break;
+            if (d >= 0 && d < ndev) devs.push_back((int)d);
+            p = (*end == ',') ? end + 1 : end;
+            if (*end != ',' && *end != 0) break;
+        }
+        if (!devs.empty()) return devs;
+    }
+    int cur = 0;
+    if (cudaGetDevice(&cur) != cudaSuccess) cur = 0;
+    devs.push_back(cur);
+    return devs;
+}
+
+// ------------------------------------------------------------------ device codec table
+struct CodecOps {
+    size_t   (*c_work)(uint32_t nchunks, uint32_t chunk);
+    uint64_t (*c_bound)(uint32_t nchunks, uint32_t chunk);
+    int      (*compress)(const void*, uint64_t, uint32_t, const uint32_t*, uint32_t, void*, void*, uint64_t*, void*);
+    size_t   (*d_work)(uint32_t nframes);
+    int      (*decompress)(const void*, const uint64_t*, const uint32_t*, uint32_t, void*, const uint64_t*, uint64_t*, uint32_t*, void*, void*);
+};
+
+
+const CodecOps* codec_ops(int codec)
+{
+    static const CodecOps lz4 = { zmt_lz4c_workspace_bytes, zmt_lz4c_out_bound, zmt_lz4_compress_device, zmt_lz4d_workspace_bytes, zmt_lz4_decompress_device };
+    static const CodecOps zstd = { zmt_zstdc_workspace_bytes, zmt_zstdc_out_bound, zmt_zstd_compress_device, zmt_zstdd_workspace_bytes, zmt_zstd_decompress_device };
+    return codec == CODEC_LZ4 ? &lz4 : &zstd;
+}
+
+// ------------------------------------------------------------------ staging slots
+struct Slot {
+    int dev = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev = nullptr;
+    uint8_t *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr, *d_work = nullptr;
+    size_t in_cap = 0, out_cap = 0, work_cap = 0, tab_cap = 0;   // tab_cap: entries in the tables below
+    // tables: pinned host mirror + device copy, one allocation each
+    uint8_t *h_tab = nullptr, *d_tab = nullptr; size_t tab_bytes = 0;
+    // batch contents
+    uint32_t n = 0;              // chunks / frames in this batch
+    size_t in_used = 0, out_used = 0;
+    int state = 0;               // 0 free, 1 filled, 2 submitted
+    bool ok = false;
+};
+
+// table layout (entries = tab_cap):  u64 a[cap+1] | u64 b[cap+1] | u64 c[cap+1] | u32 d[cap] | u32 e[cap]
+struct Tables { uint64_t *a, *b, *c; uint32_t *d, *e; };
+inline size_t tables_bytes(size_t cap) { return 3 * (cap + 1) * 8 + 2 * cap * 4 + 64; }
+inline Tables tables_at(uint8_t* base, size_t cap)
+{
+    Tables t; t.a = (uint64_t*)base; t.b = t.a + cap + 1; t.c = t.b + cap + 1; t.d = (uint32_t*)(t.c + cap + 1); t.e = t.d + cap; return t;
+}
+
+void slot_free(Slot& s)
+{
+    cudaSetDevice(s.dev);
+    if (s.stream) cudaStreamSynchronize(s.stream);
+    if (s.h_in) cudaFreeHost(s.h_in);
+    if (s.h_out) cudaFreeHost(s.h_out);
+    if (s.h_tab) cudaFreeHost(s.h_tab);
+    if (s.d_in) cudaFree(s.d_in);
+    if (s.d_out) cudaFree(s.d_out);
+    if (s.d_work) cudaFree(s.d_work);
+    if (s.d_tab) cudaFree(s.d_tab);
+    if (s.ev) cudaEventDestroy(s.ev);
+    if (s.stream) cudaStreamDestroy(s.stream);
+    s = Slot();
+}
+
+bool slot_alloc(Slot& s, int dev, size_t in_cap, size_t out_cap, size_t work_cap, size_t tab_cap)
+{
+    s.dev = dev;
+    if (cudaSetDevice(dev) != cudaSuccess) return false;
+    bool ok = true;
+    ok = ok && cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaHostAlloc((void**)&s.h_in, in_cap + 64, cudaHostAllocPortable) == cudaSuccess;
+    ok = ok && cudaHostAlloc((void**)&s.h_out, out_cap + 64, cudaHostAllocPortable) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&s.d_in, in_cap + 256) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&s.d_out, out_cap + 256) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&s.d_work, work_cap + 256) == cudaSuccess;
+    s.tab_bytes = tables_bytes(tab_cap);
+    ok = ok && cudaHostAlloc((void**)&s.h_tab, s.tab_bytes, cudaHostAllocPortable) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&s.d_tab, s.tab_bytes) == cudaSuccess;
+    s.in_cap = in_cap; s.out_cap = out_cap; s.work_cap = work_cap; s.tab_cap = tab_cap; s.ok = ok;
+    if (!ok) { cudaGetLastError(); slot_free(s); }
+    return ok;
+}
+
+// ------------------------------------------------------------------ pipeline state shared by the 3 threads
+struct Pipe {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<Slot> slots;
+    size_t fill_seq = 0, submit_seq = 0, write_seq = 0;
+    bool reader_done = false;
+    size_t error = 0;                 // first error wins
+    void fail(size_t e) { std::lock_guard<std::mutex> g(mu); if (!error) error = e; cv.notify_all(); }
+};
+
+struct Ctx {
+    int codec = 0, level = 0, threads = 0;
+    size_t inputsize = 0;
+    size_t insize = 0, outsize = 0, frames = 0, curframe = 0;
+    bool is_comp = false;
+    std::vector<int> devs;
+    Pipe pipe;
+    size_t lib_errcode = 0;
+    const ErrCodes* E = nullptr;
+};
+
+void ctx_release_slots(Ctx* c) { for (auto& s : c->pipe.slots) if (s.ok) slot_free(s); c->pipe.slots.clear(); }
+
+// ------------------------------------------------------------------ compression
+size_t compress_run(Ctx* c, GenRdWr* rw)
+{
+    const ErrCodes& E = *c->E;
+    const CodecOps* ops = codec_ops(c->codec);
+    if (!ops->compress || !ops->c_work || !ops->c_bound) { c->lib_errcode = ZMT_ST_UNSUPPORTED; return E.library; }
+    Pipe& P = c->pipe;
+    const size_t chunk = c->inputsize;
+    size_t batch_bytes = env_size("ZSTDMT_B200_BATCH_MB", 64) << 20;
+    size_t B = batch_bytes / chunk; if (B < 1) B = 1; if (B > 65536) B = 65536;
+
+    if (P.slots.empty()) {
+        c->devs = env_devices();
+        if (c->devs.empty()) { c->lib_errcode = ZMT_ST_CUDA; return E.library; }
+        int per_dev = c->threads >= 3 ? 3 : 2;
+        P.slots.resize(c->devs.size() * per_dev);
+        for (size_t i = 0; i < P.slots.size(); i++) {
+            if (!slot_alloc(P.slots[i], c->devs[i % c->devs.size()], B * chunk, (size_t)ops->c_bound((uint32_t)B, (uint32_t)chunk),
+                            ops->c_work((uint32_t)B, (uint32_t)chunk), B)) { ctx_release_slots(c); return E.mem; }
+        }
+    }
+    const size_t N = P.slots.size();
+    P.fill_seq = P.submit_seq = P.write_seq = 0; P.reader_done = false; P.error = 0;
+    for (auto& s : P.slots) s.state = 0;
+
+    // ---- reader: fills slots in sequence order (pt_compress read section, lz4-mt_compress.c:255-277)
+    std::thread reader([&]() {
+        size_t frames_read = 0; bool eof = false;
+        while (!eof) {
+            Slot* s;
+            {
+                std::unique_lock<std::mutex> lk(P.mu);
+                s = &P.slots[P.fill_seq % N];
+                P.cv.wait(lk, [&] { return s->state == 0 || P.error; });
+                if (P.error) break;
+            }
+            Tables T = tables_at(s->h_tab, s->tab_cap);
+            uint32_t n = 0; size_t got_bytes = 0;
+            while (n < B) {
+                GenBuffer b; b.buf = s->h_in + (size_t)n * chunk; b.size = chunk; b.allocated = chunk;
+                int rv = rw->fn_read(rw->arg_read, &b);
+                if (rv != 0) { P.fail(mt_error(E, rv)); eof = true; n = 0; break; }
+                if (b.size > chunk) { P.fail(E.read_fail); eof = true; n = 0; break; }
+                if (b.size == 0 && frames_read > 0) { eof = true; break; }
+                T.d[n] = (uint32_t)b.size; got_bytes += b.size; frames_read++; n++;
+            }
+            if (n == 0) break;
+            s->n = n; s->in_used = got_bytes;
+            {
+                std::lock_guard<std::mutex> g(P.mu);
+                c->insize += got_bytes; c->frames += n;
+                s->state = 1; P.fill_seq++;
+            }
+            P.cv.notify_all();
+        }
+        { std::lock_guard<std::mutex> g(P.mu); P.reader_done = true; }
+        P.cv.notify_all();
+    });
+
+    // ---- writer: in-order emission (pt_write, lz4-mt_compress.c:178-205)
+    std::thread writer([&]() {
+        for (;;) {
+            Slot* s;
+            {
+                std::unique_lock<std::mutex> lk(P.mu);
+                s = &P.slots[P.write_seq % N];
+                P.cv.wait(lk, [&] { return s->state == 2 || P.error || (P.reader_done && P.write_seq == P.fill_seq); });
+                if (P.error || s->state != 2) break;
+            }
+            cudaSetDevice(s->dev);
+            if (cudaEventSynchronize(s->ev) != cudaSuccess) { c->lib_errcode = ZMT_ST_CUDA; P.fail(E.library); break; }
+            Tables T = tables_at(s->h_tab, s->tab_cap);
+            const uint64_t total = T.a[s->n];
+            if (total > s->out_cap) { c->lib_errcode = ZMT_ST_DST_SMALL; P.fail(E.library); break; }
+            if (cudaMemcpyAsync(s->h_out, s->d_out, total, cudaMemcpyDeviceToHost, s->stream) != cudaSuccess ||
+                cudaStreamSynchronize(s->stream) != cudaSuccess) { c->lib_errcode = ZMT_ST_CUDA; P.fail(E.library); break; }
+            bool bad = false;
+            for (uint32_t i = 0; i < s->n; i++) {
+                GenBuffer b; b.buf = s->h_out + T.a[i]; b.size = (size_t)(T.a[i + 1] - T.a[i]); b.allocated = b.size;
+                int rv = rw->fn_write(rw->arg_write, &b);
+                if (rv != 0) { P.fail(mt_error(E, rv)); bad = true; break; }
+                c->outsize += b.size; c->curframe++;
+            }
+            if (bad) break;
+            { std::lock_guard<std::mutex> g(P.mu); s->state = 0; P.write_seq++; }
+            P.cv.notify_all();
+        }
+    });
+
+    // ---- submit (calling thread)
+    for (;;) {
+        Slot* s;
+        {
+            std::unique_lock<std::mutex> lk(P.mu);
+            s = &P.slots[P.submit_seq % N];
+            P.cv.wait(lk, [&] { return s->state == 1 || P.error || (P.reader_done && P.submit_seq == P.fill_seq); });
+            if (P.error || s->state != 1) break;
+        }
+        cudaSetDevice(s->dev);
+        Tables Th = tables_at(s->h_tab, s->tab_cap), Td = tables_at(s->d_tab, s->tab_cap);
+        bool full = true;
+        for (uint32_t i = 0; i < s->n; i++) if (Th.d[i] != chunk) { full = false; break; }
+        cudaError_t ce = cudaSuccess;
+        if (full) ce = cudaMemcpyAsync(s->d_in, s->h_in, (size_t)s->n * chunk, cudaMemcpyHostToDevice, s->stream);
+        else for (uint32_t i = 0; i < s->n && ce == cudaSuccess; i++)
+            if (Th.d[i]) ce = cudaMemcpyAsync(s->d_in + (size_t)i * chunk, s->h_in + (size_t)i * chunk, Th.d[i], cudaMemcpyHostToDevice, s->stream);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(Td.d, Th.d, (size_t)s->n * 4, cudaMemcpyHostToDevice, s->stream);
+        int st = ZMT_ST_CUDA;
+        if (ce == cudaSuccess) st = ops->compress(s->d_in, 0, (uint32_t)chunk, Td.d, s->n, s->d_work, s->d_out, Td.a, s->stream);
+        if (st == ZMT_ST_OK) {
+            ce = cudaMemcpyAsync(Th.a, Td.a, ((size_t)s->n + 1) * 8, cudaMemcpyDeviceToHost, s->stream);
+            if (ce == cudaSuccess) ce = cudaEventRecord(s->ev, s->stream);
+            if (ce != cudaSuccess) st = ZMT_ST_CUDA;
+        }
+        if (st != ZMT_ST_OK) { c->lib_errcode = (size_t)st; P.fail(E.library); break; }
+        { std::lock_guard<std::mutex> g(P.mu); s->state = 2; P.submit_seq++; }
+        P.cv.notify_all();
+    }
+    reader.join(); writer.join();
+    for (auto& s : P.slots) { cudaSetDevice(s.dev); cudaStreamSynchronize(s.stream); }
+    return P.error;
+}
+
+// ------------------------------------------------------------------ decompression
+// Output size of one payload, from its own header (pt_decompress sizes the buffer from
+// LE64 @ payload+6, lz4-mt_decompress.c:329-335; zstd: frame content size).
+// Returns false if the header is unusable.
+bool lz4f_out_size(const uint8_t* p, size_t n, size_t frame_idx, uint64_t* out)
+{
+    if (n < 7 || rd32(p) != LZ4F_MAGIC) { *out = 0; return true; }     // the device decoder reports the precise status
+    const uint32_t flg = p[4], bd = p[5];
+    if (flg & 0x08) { if (n < 15) return false; *out = rd64(p + 6); return true; }
+    (void)frame_idx;
+    // no content-size field: bound it by walking the block headers (each block <= blockMaxSize)
+    const uint32_t id = (bd >> 4) & 7; if (id < 4) return false;
+    const uint64_t blkmax = 1ull << (8 + 2 * id);
+    size_t pos = 4 + 2 + ((flg & 1) ? 4 : 0) + 1; uint64_t total = 0;
+    while (pos + 4 <= n) {
+        const uint32_t bh = rd32(p + pos); pos += 4;
+        if (bh == 0) break;
+        const uint32_t bs = bh & 0x7FFFFFFFu;
+        total += (bh & 0x80000000u) ? bs : blkmax;
+        pos += bs + ((flg & 0x10) ? 4 : 0);
+    }
+    *out = total; return true;
+}
+
+bool zstd_out_size(const uint8_t* p, size_t n, uint64_t* out)
+{
+    if (n < 6 || rd32(p) != ZSTD_MAGIC) return false;
+    const uint32_t fhd = p[4], fcs = fhd >> 6, single = (fhd >> 5) & 1, did = fhd & 3;
+    size_t pos = 5 + (single ? 0 : 1) + (did == 0 ? 0 : did == 1 ? 1 : did == 2 ? 2 : 4);
+    const size_t fl = fcs == 0 ? (single ? 1 : 0) : fcs == 1 ? 2 : fcs == 2 ? 4 : 8;
+    if (fl == 0 || n < pos + fl) return false;
+    if (fl == 1) *out = p[pos]; else if (fl == 2) *out = (uint64_t)(p[pos] | (p[pos + 1] << 8)) + 256; else if (fl == 4) *out = rd32(p + pos); else *out = rd64(p + pos);
+    return true;
+}
+
+// reads exactly `want` bytes unless EOF; returns 0 ok / error; *got = delivered
+size_t read_some(const ErrCodes& E, GenRdWr* rw, void* dst, size_t want, size_t* got)
+{
+    GenBuffer b; b.buf = dst; b.size = want; b.allocated = want;
+    int rv = rw->fn_read(rw->arg_read, &b);
+    if (rv != 0) return mt_error(E, rv);
+    if (b.size > want) return E.read_fail;
+    *got = b.size; return 0;
+}
+
+size_t decompress_run(Ctx* c, GenRdWr* rw)
+{
+    const ErrCodes& E = *c->E;
+    const CodecOps* ops = codec_ops(c->codec);
+    if (!ops->decompress || !ops->d_work) { c->lib_errcode = ZMT_ST_UNSUPPORTED; return E.library; }
+    Pipe& P = c->pipe;
+    const size_t in_cap0 = (env_size("ZSTDMT_B200_BATCH_MB", 64) << 20), out_cap0 = in_cap0 * 2, tab_cap = 8192;
+
+    // ---- stream-type sniffing on the calling thread (LZ4MT_decompressDCtx, lz4-mt_decompress.c:503-520;
+    //      ZSTDCB_decompressDCtx, zstd-mt_decompress.c:721-759)
+    uint8_t first[16]; size_t have = 0, got = 0;
+    bool hdr_pending = false;                 // first 12-byte header already (partly) read into `first`
+    size_t first_payload_have = 0;            // zstd pzstd-style: 4 payload bytes already read
+    if (c->codec == CODEC_LZ4) {
+        size_t e = read_some(E, rw, first, 4, &got); if (e) return e;
+        if (got != 4) return E.data_error;
+        if (rd32(first) != MT_MAGIC_SKIPPABLE) {
+            if (rd32(first) != LZ4F_MAGIC) return E.data_error;
+            c->lib_errcode = ZMT_ST_UNSUPPORTED; return E.library;     // plain .lz4 stream: SURVEY §8(f) row 2, not built yet
+        }
+        e = read_some(E, rw, first + 4, 8, &got); if (e) return e;
+        if (got != 8) return E.read_fail;
+        have = 12; hdr_pending = true;
+    } else {
+        size_t e = read_some(E, rw, first, 16, &got); if (e) return e;
+        have = got;
+        auto is_zstd = [](const uint8_t* p) { uint32_t m = rd32(p); return m >= 0xFD2FB522u && m <= 0xFD2FB528u; };
+        auto is_skip = [](const uint8_t* p) { return rd32(p) == MT_MAGIC_SKIPPABLE && rd32(p + 4) == 4; };
+        if (have < 16) {
+            if (have < 4 || !is_zstd(first)) return E.data_error;
+            if (have == 9) return 0;                                   // empty file (zstd-mt_decompress.c:735-740)
+            c->lib_errcode = ZMT_ST_UNSUPPORTED; return E.library;     // plain zstd stream: §8(f) row 2
+        }
+        c->insize += 16;
+        if (is_skip(first) && is_zstd(first + 12)) { hdr_pending = true; first_payload_have = 4; }          // pzstd style
+        else if (is_zstd(first) && is_skip(first + 9)) {                                                       // zstdmt style: 9-byte empty frame + 12-byte header
+            uint8_t tmp[12]; memcpy(tmp, first + 9, 7);
+            size_t e2 = read_some(E, rw, tmp + 7, 5, &got); if (e2) return e2;
+            if (got != 5) return E.data_error;
+            c->insize += 5; memcpy(first, tmp, 12); hdr_pending = true; first_payload_have = 0;
+        } else if (is_zstd(first)) { c->lib_errcode = ZMT_ST_UNSUPPORTED; return E.library; }
+        else return E.data_error;
+    }
+
+    if (P.slots.empty()) {
+        c->devs = env_devices();
+        if (c->devs.empty()) { c->lib_errcode = ZMT_ST_CUDA; return E.library; }
+        int per_dev = c->threads >= 3 ? 3 : 2;
+        P.slots.resize(c->devs.size() * per_dev);
+        for (size_t i = 0; i < P.slots.size(); i++)
+            if (!slot_alloc(P.slots[i], c->devs[i % c->devs.size()], in_cap0, out_cap0, ops->d_work((uint32_t)tab_cap), tab_cap)) { ctx_release_slots(c); return E.mem; }
+    }
+    const size_t N = P.slots.size();
+    P.fill_seq = P.submit_seq = P.write_seq = 0; P.reader_done = false; P.error = 0;
+    for (auto& s : P.slots) s.state = 0;
+
+    // ---- reader (pt_read, lz4-mt_decompress.c:192-281 / zstd-mt_decompress.c:209-369)
+    std::thread reader([&]() {
+        bool eof = false;
+        std::vector<uint8_t> carry;              // a frame that did not fit the previous slot
+        uint64_t carry_out = 0;
+        while (!eof) {
+            Slot* s;
+            {
+                std::unique_lock<std::mutex> lk(P.mu);
+                s = &P.slots[P.fill_seq % N];
+                P.cv.wait(lk, [&] { return s->state == 0 || P.error; });
+                if (P.error) break;
+            }
+            Tables T = tables_at(s->h_tab, s->tab_cap);
+            uint32_t n = 0; size_t in_used = 0; uint64_t out_used = 0; size_t stat_in = 0;
+            bool failed = false;
+            auto grow = [&](size_t need_in, uint64_t need_out) -> bool {   // empty slot too small for one frame: reallocate it
+                if (need_in <= s->in_cap && need_out <= s->out_cap) return true;
+                const int dev = s->dev; const size_t nin = need_in > s->in_cap ? need_in : s->in_cap, nout = need_out > s->out_cap ? (size_t)need_out : s->out_cap;
+                const size_t wk = s->work_cap, tc = s->tab_cap;
+                slot_free(*s);
+                return slot_alloc(*s, dev, nin, nout, wk, tc);
+            };
+            if (!carry.empty()) {
+                if (!grow(carry.size(), carry_out)) { P.fail(E.mem); break; }
+                T = tables_at(s->h_tab, s->tab_cap);
+                memcpy(s->h_in, carry.data(), carry.size());
+                T.a[0] = 0; T.d[0] = (uint32_t)(carry.size() - 12); T.b[0] = 0;
+                in_used = carry.size(); out_used = carry_out; n = 1; carry.clear();
+            }
+            while (n < s->tab_cap) {
+                uint8_t hdr[12]; size_t pre = 0;
+                if (hdr_pending) { memcpy(hdr, first, 12); hdr_pending = false; pre = first_payload_have; if (c->codec == CODEC_LZ4) stat_in += 0; }
+                else {
+                    size_t g = 0; size_t e = read_some(E, rw, hdr, 12, &g);
+                    if (e) { P.fail(e); failed = true; break; }
+                    if (g == 0) { eof = true; break; }
+                    if (g != 12) { P.fail(E.read_fail); failed = true; break; }
+                    if (rd32(hdr) != MT_MAGIC_SKIPPABLE) { P.fail(E.data_error); failed = true; break; }
+                    if (c->codec == CODEC_ZSTD) stat_in += 12;
+                }
+                if (rd32(hdr + 4) != 4) { P.fail(E.data_error); failed = true; break; }
+                if (c->codec == CODEC_LZ4) stat_in += 12;
+                const size_t toRead = rd32(hdr + 8);
+                if (toRead < pre) { P.fail(E.data_error); failed = true; break; }
+                // where to put it: current slot if it fits, else a temporary carry buffer
+                uint8_t* dstp; bool to_carry = false;
+                if (in_used + 12 + toRead <= s->in_cap) dstp = s->h_in + in_used;
+                else if (n == 0) { if (!grow(12 + toRead, 0)) { P.fail(E.mem); failed = true; break; } T = tables_at(s->h_tab, s->tab_cap); dstp = s->h_in; }
+                else { carry.resize(12 + toRead); dstp = carry.data(); to_carry = true; }
+                memcpy(dstp, hdr, 12);
+                if (pre) memcpy(dstp + 12, first + 12, pre);
+                size_t g = 0; size_t e = read_some(E, rw, dstp + 12 + pre, toRead - pre, &g);
+                if (e) { P.fail(e); failed = true; break; }
+                if (g != toRead - pre) { P.fail(E.data_error); failed = true; break; }
+                stat_in += g;
+                uint64_t osz = 0; bool okh = c->codec == CODEC_LZ4 ? lz4f_out_size(dstp + 12, toRead, c->frames + n, &osz) : zstd_out_size(dstp + 12, toRead, &osz);
+                if (!okh) { c->lib_errcode = ZMT_ST_BAD_HEADER; P.fail(c->codec == CODEC_LZ4 ? E.library : E.library); failed = true; break; }
+                if (to_carry) { carry_out = osz; break; }
+                if (out_used + osz > s->out_cap) {
+                    if (n == 0) {
+                        // single frame larger than the slot: grow (payload already sits in h_in -> save it first)
+                        std::vector<uint8_t> save(dstp, dstp + 12 + toRead);
+                        if (!grow(12 + toRead, osz)) { P.fail(E.mem); failed = true; break; }
+                        T = tables_at(s->h_tab, s->tab_cap);
+                        memcpy(s->h_in, save.data(), save.size());
+                    } else { carry.assign(dstp, dstp + 12 + toRead); carry_out = osz; break; }
+                }
+                T.a[n] = in_used; T.d[n] = (uint32_t)toRead; T.b[n] = out_used;
+                in_used += 12 + toRead; out_used += osz; n++;
+            }
+            if (failed) break;
+            if (n == 0) break;
+            T.b[n] = out_used;
+            s->n = n; s->in_used = in_used; s->out_used = (size_t)out_used;
+            {
+                std::lock_guard<std::mutex> g(P.mu);
+                c->insize += stat_in; c->frames += n;
+                s->state = 1; P.fill_seq++;
+            }
+            P.cv.notify_all();
+        }
+        { std::lock_guard<std::mutex> g(P.mu); P.reader_done = true; }
+        P.cv.notify_all();
+    });
+
+    // ---- writer (pt_write, lz4-mt_decompress.c:165-187)
+    std::thread writer([&]() {
+        for (;;) {
+            Slot* s;
+            {
+                std::unique_lock<std::mutex> lk(P.mu);
+                s = &P.slots[P.write_seq % N];
+                P.cv.wait(lk, [&] { return s->state == 2 || P.error || (P.reader_done && P.write_seq == P.fill_seq); });
+                if (P.error || s->state != 2) break;
+            }
+            cudaSetDevice(s->dev);
+            if (cudaEventSynchronize(s->ev) != cudaSuccess) { c->lib_errcode = ZMT_ST_CUDA; P.fail(E.library); break; }
+            Tables T = tables_at(s->h_tab, s->tab_cap);
+            bool bad = false;
+            for (uint32_t i = 0; i < s->n; i++) {
+                const uint32_t st = T.e[i];
+                if (st != ZMT_ST_OK) {
+                    c->lib_errcode = st;
+                    P.fail((st == ZMT_ST_TRUNCATED || st == ZMT_ST_TRAILING) ? E.frame_decompress : E.library);
+                    bad = true; break;
+                }
+                GenBuffer b; b.buf = s->h_out + T.b[i]; b.size = (size_t)T.c[i]; b.allocated = b.size;
+                int rv = rw->fn_write(rw->arg_write, &b);
+                if (rv != 0) { P.fail(mt_error(E, rv)); bad = true; break; }
+                c->outsize += b.size; c->curframe++;
+            }
+            if (bad) break;
+            { std::lock_guard<std::mutex> g(P.mu); s->state = 0; P.write_seq++; }
+            P.cv.notify_all();
+        }
+    });
+
+    // ---- submit
+    for (;;) {
+        Slot* s;
+        {
+            std::unique_lock<std::mutex> lk(P.mu);
+            s = &P.slots[P.submit_seq % N];
+            P.cv.wait(lk, [&] { return s->state == 1 || P.error || (P.reader_done && P.submit_seq == P.fill_seq); });
+            if (P.error || s->state != 1) break;
+        }
+        cudaSetDevice(s->dev);
+        Tables Th = tables_at(s->h_tab, s->tab_cap), Td = tables_at(s->d_tab, s->tab_cap);
+        cudaError_t ce = cudaMemcpyAsync(s->d_in, s->h_in, s->in_used, cudaMemcpyHostToDevice, s->stream);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(s->d_tab, s->h_tab, s->tab_bytes, cudaMemcpyHostToDevice, s->stream);
+        int st = ZMT_ST_CUDA;
+        if (ce == cudaSuccess) st = ops->decompress(s->d_in, Td.a, Td.d, s->n, s->d_out, Td.b, Td.c, Td.e, s->d_work, s->stream);
+        if (st == ZMT_ST_OK) {
+            if (s->out_used) ce = cudaMemcpyAsync(s->h_out, s->d_out, s->out_used, cudaMemcpyDeviceToHost, s->stream);
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(Th.c, Td.c, (size_t)s->n * 8, cudaMemcpyDeviceToHost, s->stream);
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(Th.e, Td.e, (size_t)s->n * 4, cudaMemcpyDeviceToHost, s->stream);
+            if (ce == cudaSuccess) ce = cudaEventRecord(s->ev, s->stream);
+            if (ce != cudaSuccess) st = ZMT_ST_CUDA;
+        }
+        if (st != ZMT_ST_OK) { c->lib_errcode = (size_t)st; P.fail(E.library); break; }
+        { std::lock_guard<std::mutex> g(P.mu); s->state = 2; P.submit_seq++; }
+        P.cv.notify_all();
+    }
+    reader.join(); writer.join();
+    for (auto& s : P.slots) { if (s.ok) { cudaSetDevice(s.dev); cudaStreamSynchronize(s.stream); } }
+    return P.error;
+}
+
+// ------------------------------------------------------------------ context helpers
+Ctx* ctx_new(int codec, bool comp, int threads, int level, size_t inputsize)
+{
+    Ctx* c = new (std::nothrow) Ctx();
+    if (!c) return nullptr;
+    c->codec = codec; c->is_comp = comp; c->threads = threads; c->level = level; c->inputsize = inputsize;
+    c->E = codec == CODEC_LZ4 ? &kErrLz4 : &kErrZstd;
+    return c;
+}
+void ctx_delete(Ctx* c) { if (!c) return; ctx_release_slots(c); delete c; }
+
+const char* status_string(size_t st)
+{
+    switch (st) {
+    case ZMT_ST_TRUNCATED: return "frame truncated";
+    case ZMT_ST_BAD_MAGIC: return "ERROR_frameType_unknown";
+    case ZMT_ST_BAD_HEADER: return "ERROR_frameHeader_incomplete";
+    case ZMT_ST_HDR_CHECKSUM: return "ERROR_headerChecksum_invalid";
+    case ZMT_ST_BLOCK: return "ERROR_decompressionFailed";
+    case ZMT_ST_DST_SMALL: return "ERROR_dstMaxSize_tooSmall";
+    case ZMT_ST_CONTENT_CHECKSUM: return "ERROR_contentChecksum_invalid";
+    case ZMT_ST_CONTENT_SIZE: return "ERROR_frameSize_wrong";
+    case ZMT_ST_TRAILING: return "trailing bytes after frame";
+    case ZMT_ST_UNSUPPORTED: return "stream type not supported by the B200 path";
+    case ZMT_ST_CUDA: return "CUDA runtime / kernel failure";
+    case ZMT_ST_BAD_ARG: return "bad argument";
+    }
+    return nullptr;
+}
+
+const char* error_string(bool lz4, size_t code, size_t lib_errcode)
+{
+    static const char* none = nullptr;
+    (void)none;
+    const size_t neg = 0 - code;
+    // the reference returns the codec library's own message whenever its global errcode is set
+    // (lz4-mt_common.c:37-38); we own the status table instead of liblz4 / libzstd
+    if (lib_errcode && status_string(lib_errcode) && neg == (lz4 ? 8u : 9u)) return status_string(lib_errcode);
+    static const char* lz4s[] = { "No error detected", "Allocation error : not enough memory", "Read failure", "Write failure", "Malformed input",
+                                  "Could not compress frame at once", "Could not decompress frame at once", "Compression parameter is out of bound",
+                                  "Compression library reports failure" };
+    static const char* zs[] = { "No error detected", "Allocation error : not enough memory", nullptr, "Read failure", "Write failure", "Malformed input",
+                                "Could not compress frame at once", "Could not decompress frame at once", "Compression parameter is out of bound",
+                                "Compression library reports failure" };
+    if (lz4) { if (neg < 9) return lz4s[neg]; return "Unspecified lz4mt error code"; }
+    if (neg < 10 && zs[neg]) return zs[neg];
+    return "Unspecified zstmt error code";
+}
+
+}  // namespace
+
+// =================================================================== exported C ABI
+extern "C" {
+
+size_t lz4mt_errcode = 0;      // lib/lz4-mt_common.c:16
+size_t zstdmt_errcode = 0;     // lib/zstd-mt_common.c:19
+
+// ---------------- LZ4MT_*
+unsigned LZ4MT_isError(size_t code) { return code > (size_t)-10; }                     // lz4-mt_common.c:25-28 (maxCode = 10)
+const char* LZ4MT_getErrorString(size_t code) { return error_string(true, code, lz4mt_errcode); }
+
+void* LZ4MT_createCCtx(int threads, int level, int inputsize)                          // lz4-mt_compress.c:92-156
+{
+    if (threads < 1 || threads > 128) return nullptr;
+    if (level < 1 || level > 12) return nullptr;
+    if (inputsize < 0) return nullptr;
+    return ctx_new(CODEC_LZ4, true, threads, level, inputsize ? (size_t)inputsize : (size_t)4 << 20);
+}
+size_t LZ4MT_compressCCtx(void* ctx, void* rdwr)                                       // lz4-mt_compress.c:312-353
+{
+    Ctx* c = (Ctx*)ctx;
+    if (!c) return kErrLz4.param;
+    if (!rdwr) return kErrLz4.param;
+    size_t r = compress_run(c, (GenRdWr*)rdwr);
+    if (c->lib_errcode) lz4mt_errcode = c->lib_errcode;
+    return r;
+}
+size_t LZ4MT_GetFramesCCtx(void* ctx) { return ctx ? ((Ctx*)ctx)->curframe : 0; }     // lz4-mt_compress.c:374-380
+size_t LZ4MT_GetInsizeCCtx(void* ctx) { return ctx ? ((Ctx*)ctx)->insize : 0; }
+size_t LZ4MT_GetOutsizeCCtx(void* ctx) { return ctx ? ((Ctx*)ctx)->outsize : 0; }
+void LZ4MT_freeCCtx(void* ctx) { ctx_delete((Ctx*)ctx); }
+
+void* LZ4MT_createDCtx(int threads, int inputsize)                                     // lz4-mt_decompress.c:90-142
+{
+    if (threads < 1 || threads > 128) return nullptr;
+    if (inputsize < 0) return nullptr;
+    return ctx_new(CODEC_LZ4, false, threads, 0, inputsize ? (size_t)inputsize : (size_t)64 << 10);
+}
+size_t LZ4MT_decompressDCtx(void* ctx, void* rdwr)                                     // lz4-mt_decompress.c:485-567
+{
+    Ctx* c = (Ctx*)ctx;
+    if (!c || !rdwr) return kErrLz4.param;
+    size_t r = decompress_run(c, (GenRdWr*)rdwr);
+    if (c->lib_errcode) lz4mt_errcode = c->lib_errcode;
+    return r;
+}
+size_t LZ4MT_GetFramesDCtx(void* ctx) { return ctx ? ((Ctx*)ctx)->curframe : 0; }
+size_t LZ4MT_GetInsizeDCtx(void* ctx) { return ctx ? ((Ctx*)ctx)->insize : 0; }
+size_t LZ4MT_GetOutsizeDCtx(void* ctx) { return ctx ? ((Ctx*)ctx)->outsize : 0; }
+void LZ4MT_freeDCtx(void* ctx) { ctx_delete((Ctx*)ctx); }
+
+// ---------------- ZSTDCB_*
+unsigned ZSTDCB_isError(size_t code) { return code > (size_t)-11; }                    // zstd-mt_common.c:26-29 (maxCode = 11)
+const char* ZSTDCB_getErrorString(size_t code) { return error_string(false, code, zstdmt_errcode); }
+
+void* ZSTDCB_createCCtx(int threads, int level, int inputsize)                         // zstd-mt_compress.c:94-155
+{
+    if (threads < 1 || threads > 128) return nullptr;
+    if (level < 1 || level > 22) return nullptr;
+    if (inputsize < 0) return nullptr;
+    size_t chunk = (size_t)inputsize;
+    if (!chunk) {
+        // the reference indexes its table by `level`, not level-1 (zstd-mt_compress.c:119-127); level 22 reads past
+        // the end there — we clamp to the last entry instead of replicating the overrun
+        static const int windowLog[] = { 19, 19, 20, 20, 20, 21, 21, 21, 21, 21, 22, 22, 22, 22, 22, 23, 23, 23, 23, 25, 26, 27 };
+        int idx = level > 21 ? 21 : level;
+        chunk = (size_t)1 << (windowLog[idx] + 1);
+        if (chunk > ((size_t)1 << 30)) chunk = (size_t)1 << 30;     // keep int-sized like the reference's int inputsize
+    }
+    return ctx_new(CODEC_ZSTD, true, threads, level, chunk);
+}
+size_t ZSTDCB_compressCCtx(void* ctx, void* rdwr)                                      // zstd-mt_compress.c:322-392
+{
+    Ctx* c = (Ctx*)ctx;
+    if (!c) return kErrZstd.init_missing;
+    if (!rdwr) return kErrZstd.param;
+    c->insize = c->outsize = c->frames = c->curframe = 0;                               // counters reset per call (:337-341)
+    c->lib_errcode = 0;
+    size_t r = compress_run(c, (GenRdWr*)rdwr);
+    if (c->lib_errcode) zstdmt_errcode = c->lib_errcode;
+    return r;
+}
+size_t ZSTDCB_GetFramesCCtx(void* ctx) { return ctx ? ((Ctx*)ctx)->curframe : kErrZstd.init_missing; }  // :395-420
+size_t ZSTDCB_GetInsizeCCtx(void* ctx) { return ctx ? ((Ctx*)ctx)->insize : kErrZstd.init_missing; }
+size_t ZSTDCB_GetOutsizeCCtx(void* ctx) { return ctx ? ((Ctx*)ctx)->outsize : kErrZstd.init_missing; }
+void ZSTDCB_freeCCtx(void* ctx) { ctx_delete((Ctx*)ctx); }
+
+void* ZSTDCB_createDCtx(int threads, int inputsize)                                    // zstd-mt_decompress.c:105-139
+{
+    if (threads < 1 || threads > 128) return nullptr;
+    if (inputsize < 0) return nullptr;
+    return ctx_new(CODEC_ZSTD, false, threads, 0, inputsize ? (size_t)inputsize : (size_t)512 << 10);
+}
+size_t ZSTDCB_decompressDCtx(void* ctx, void* rdwr)                                    // zstd-mt_decompress.c:693-843
+{
+    Ctx* c = (Ctx*)ctx;
+    if (!c || !rdwr) return kErrZstd.param;
+    size_t r = decompress_run(c, (GenRdWr*)rdwr);
+    if (c->lib_errcode) zstdmt_errcode = c->lib_errcode;
+    return r;
+}
+size_t ZSTDCB_GetFramesDCtx(void* ctx) { return ctx ? ((Ctx*)ctx)->curframe : 0; }    // :845-869
+size_t ZSTDCB_GetInsizeDCtx(void* ctx) { return ctx ? ((Ctx*)ctx)->insize : 0; }
+size_t ZSTDCB_GetOutsizeDCtx(void* ctx) { return ctx ? ((Ctx*)ctx)->outsize : 0; }
+void ZSTDCB_freeDCtx(void* ctx) { ctx_delete((Ctx*)ctx); }
+
+// ---------------- ZSTDMT_* spellings (lib/README.md:43-76)
+unsigned ZSTDMT_isError(size_t code) { return ZSTDCB_isError(code); }
+const char* ZSTDMT_getErrorString(size_t code) { return ZSTDCB_getErrorString(code); }
+void* ZSTDMT_createCCtx(int t, int l, int i) { return ZSTDCB_createCCtx(t, l, i); }
+size_t ZSTDMT_compressCCtx(void* c, void* r) { return ZSTDCB_compressCCtx(c, r); }
+size_t ZSTDMT_GetFramesCCtx(void* c) { return ZSTDCB_GetFramesCCtx(c); }
+size_t ZSTDMT_GetInsizeCCtx(void* c) { return ZSTDCB_GetInsizeCCtx(c); }
+size_t ZSTDMT_GetOutsizeCCtx(void* c) { return ZSTDCB_GetOutsizeCCtx(c); }
+void ZSTDMT_freeCCtx(void* c) { ZSTDCB_freeCCtx(c); }
+void* ZSTDMT_createDCtx(int t, int i) { return ZSTDCB_createDCtx(t, i); }
+size_t ZSTDMT_decompressDCtx(void* c, void* r) { return ZSTDCB_decompressDCtx(c, r); }
+size_t ZSTDMT_GetFramesDCtx(void* c) { return ZSTDCB_GetFramesDCtx(c); }
+size_t ZSTDMT_GetInsizeDCtx(void* c) { return ZSTDCB_GetInsizeDCtx(c); }
+size_t ZSTDMT_GetOutsizeDCtx(void* c) { return ZSTDCB_GetOutsizeDCtx(c); }
+void ZSTDMT_freeDCtx(void* c) { ZSTDCB_freeDCtx(c); }
+
+}  // extern "C"
