@@ -122,14 +122,12 @@ static uint8_t* put_len(uint8_t* op, size_t len)   /* len already reduced by 15 
     return op;
 }
 
-size_t orc_lz4_block_compress_b200(const uint8_t* src, size_t n, uint8_t* dst, size_t dstCap)
+/* candidate offsets for every position of a block (0 = no match); exported for tests/tools */
+void orc_lz4_b200_offsets(const uint8_t* src, size_t n, uint16_t* off)
 {
     uint32_t* table = (uint32_t*)calloc((size_t)1 << B200_HASHLOG, sizeof(uint32_t));
-    uint16_t* off = (uint16_t*)calloc(n ? n : 1, sizeof(uint16_t));
-    uint8_t* op = dst;
-    size_t i, r, anchor = 0, p = 0;
-    if (dstCap < orc_lz4_block_bound(n) || n > 65536) { free(table); free(off); return 0; }
-
+    size_t i, r;
+    memset(off, 0, n * sizeof(uint16_t));
     for (r = 0; r < n; r += B200_ROUND) {
         size_t rend = r + B200_ROUND < n ? r + B200_ROUND : n;
         for (i = r; i < rend; i++) {
@@ -152,6 +150,16 @@ size_t orc_lz4_block_compress_b200(const uint8_t* src, size_t n, uint8_t* dst, s
     }
     /* note: position j in the local window that is itself not eligible can never be < an
      * eligible i (eligibility is a prefix property), so no eligibility test on j is needed. */
+    free(table);
+}
+
+size_t orc_lz4_block_compress_b200(const uint8_t* src, size_t n, uint8_t* dst, size_t dstCap)
+{
+    uint16_t* off = (uint16_t*)calloc(n ? n : 1, sizeof(uint16_t));
+    uint8_t* op = dst;
+    size_t anchor = 0, p = 0;
+    if (dstCap < orc_lz4_block_bound(n) || n > 65536) { free(off); return 0; }
+    orc_lz4_b200_offsets(src, n, off);
 
     while (p < n) {
         size_t q = p, L, c, lit;
@@ -175,7 +183,7 @@ size_t orc_lz4_block_compress_b200(const uint8_t* src, size_t n, uint8_t* dst, s
         if (lit >= 15) { *tok = 0xF0; op = put_len(op, lit - 15); } else *tok = (uint8_t)(lit << 4);
         memcpy(op, src + anchor, lit); op += lit;
     }
-    free(table); free(off);
+    free(off);
     return (size_t)(op - dst);
 }
 

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libzstdmt_b200.so")
+LIB_PATH = os.environ.get("ZMT_LIB") or os.path.join(_HERE, "libzstdmt_b200.so")
 
 c_sz = ctypes.c_size_t
 c_u64 = ctypes.c_uint64

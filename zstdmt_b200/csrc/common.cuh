@@ -132,6 +132,7 @@ __device__ __forceinline__ uint32_t block_exscan(uint32_t v, uint32_t* ws, uint3
     uint32_t inc = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(ZMT_FULL_MASK, inc, d); if (lane >= (uint32_t)d) inc += y; }
+    __syncwarp();
     __syncthreads();
     if (lane == 31) ws[wid] = inc;
     __syncthreads();

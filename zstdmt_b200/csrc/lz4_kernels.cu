@@ -17,6 +17,8 @@
 //
 // The compressor's match/parse rule is deterministic and restated on the CPU in
 // oracle/lz4_oracle.c:orc_lz4_block_compress_b200 (tests compare bit-exact).
+#include <stdio.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "zmt_dev.h"
 
@@ -29,6 +31,11 @@ __device__ __forceinline__ uint64_t zmt_chunk_len(const uint32_t* __restrict__ c
     if (in_bytes <= base) return 0;
     return (in_bytes - base) < chunk_size ? (in_bytes - base) : chunk_size;
 }
+
+// A CTA barrier preceded by a warp reconvergence: the data-dependent phases leave warps split into
+// independently scheduled groups, and an aligned BAR.SYNC + the uniform-datapath branches ptxas places
+// after it (BRA.U) must only ever be executed by whole warps (else: 'illegal instruction' on sm_100).
+#define CTA_SYNC() do { __syncwarp(); __syncthreads(); } while (0)
 
 // ============================================================================ compressor
 #define LZ4_BLK      65536u
@@ -81,23 +88,28 @@ __device__ __forceinline__ uint32_t c_match_len(const uint8_t* s, uint32_t q, ui
 template <int MODE>
 __device__ __forceinline__ void c_walk(CompressSmem& S, uint32_t k, uint32_t p, uint32_t t0, uint32_t limit)
 {
+    // Single-exit loop (no returns from inside): divergent lanes leave through one reconvergence
+    // point, so the warp is whole again before the CTA barrier that follows every call.
     const uint32_t t1 = t0 + C_TILE;
-    for (;;) {
-        if (p >= t1) { if (MODE == 1) { S.link[k] = C_END; S.mpos[k] = p; } if (MODE == 0) S.xfree[k] = p; return; }
-        uint32_t rel = p - t0, j = rel / C_SEG;
-        if (MODE == 0 && j != k) { S.xfree[k] = p; return; }
-        if (MODE != 0 && j != k && (rel & (C_SEG - 1)) == 0) { if (MODE == 1) { S.link[k] = (uint16_t)j; S.mpos[k] = p; } return; }
+    uint32_t lk = 0xFFFFFFFFu, mp = 0;          // result: link / merge position (MODE 1), exit (MODE 0)
+    bool done = false;
+    while (!done) {
+        if (p >= t1) { lk = C_END; mp = p; done = true; continue; }
+        const uint32_t rel = p - t0, j = rel / C_SEG;
+        if (MODE == 0 && j != k) { mp = p; done = true; continue; }
+        if (MODE != 0 && j != k && (rel & (C_SEG - 1)) == 0) { lk = j; mp = p; done = true; continue; }
         uint32_t bits = (S.M[rel >> 5] >> (rel & 16)) & 0xFFFFu;     // this segment's 16 bits
         bits &= 0xFFFFu << (rel & 15);
         if (!bits) {                                                   // segment exhausted -> free position at its end
-            uint32_t nx = t0 + (j + 1) * C_SEG;
-            if (MODE == 0) { S.xfree[k] = nx; return; }
-            if (j + 1 == C_NT) { if (MODE == 1) { S.link[k] = C_END; S.mpos[k] = t1; } return; }
-            if (j != k) { if (MODE == 1) { S.link[k] = (uint16_t)(j + 1); S.mpos[k] = nx; } return; }
-            p = nx; continue;                                          // MODE 2 inside own segment
+            const uint32_t nx = t0 + (j + 1) * C_SEG;
+            if (MODE == 0) { mp = nx; done = true; }
+            else if (j + 1 == C_NT) { lk = C_END; mp = t1; done = true; }
+            else if (j != k) { lk = j + 1; mp = nx; done = true; }
+            else p = nx;                                               // MODE 2 inside own segment
+            continue;
         }
-        uint32_t qr = (rel & ~15u) + (__ffs(bits) - 1), q = t0 + qr;
-        if (MODE != 0 && j != k && ((S.V[qr >> 5] >> (qr & 31)) & 1)) { if (MODE == 1) { S.link[k] = (uint16_t)j; S.mpos[k] = q; } return; }
+        const uint32_t qr = (rel & ~15u) + (__ffs(bits) - 1), q = t0 + qr;
+        if (MODE != 0 && j != k && ((S.V[qr >> 5] >> (qr & 31)) & 1)) { lk = j; mp = q; done = true; continue; }
         uint32_t L;
         if (MODE == 2) { atomicOr(&S.Sel[qr >> 5], 1u << (qr & 31)); L = S.len[qr]; }
         else {
@@ -107,6 +119,8 @@ __device__ __forceinline__ void c_walk(CompressSmem& S, uint32_t k, uint32_t p, 
         }
         p = q + L;
     }
+    if (MODE == 0) S.xfree[k] = mp;
+    if (MODE == 1) { S.link[k] = (uint16_t)lk; S.mpos[k] = mp; }
 }
 
 __device__ __forceinline__ uint32_t c_seq_size(uint32_t lit, uint32_t L)
@@ -117,9 +131,12 @@ __device__ __forceinline__ uint32_t c_seq_size(uint32_t lit, uint32_t L)
     return s;
 }
 
-__global__ void __launch_bounds__(C_NT, 2)
+#ifndef ZMT_DBG_OCC
+#define ZMT_DBG_OCC 2
+#endif
+__global__ void __launch_bounds__(C_NT, ZMT_DBG_OCC)
 lz4_compress_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32_t chunk_size, const uint32_t* __restrict__ chunk_bytes,
-                           uint32_t bpc, uint8_t* __restrict__ tmp, uint32_t* __restrict__ blk_csize, uint32_t nblocks)
+                           uint32_t bpc, uint8_t* __restrict__ tmp, uint32_t* __restrict__ blk_csize, uint32_t nblocks, uint32_t flags)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     CompressSmem& S = *reinterpret_cast<CompressSmem*>(smem_raw);
@@ -137,13 +154,13 @@ lz4_compress_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, ui
         uint8_t* dst = tmp + (uint64_t)blk * ZMT_LZ4_TMP_STRIDE;
 
         // ---- stage the block into shared memory (TMA bulk copy when 16-byte aligned)
-        __syncthreads();                                  // previous block fully consumed
-        const uint32_t nb16 = (((uintptr_t)src & 15) == 0) ? (n & ~15u) : 0;
+        CTA_SYNC();                                  // previous block fully consumed
+        const uint32_t nb16 = ((((uintptr_t)src & 15) == 0) && !(flags & 1)) ? (n & ~15u) : 0;
         if (tid == 0) {
             mbar_init(&S.mbar, 1);
             S.nlong = 0;
         }
-        __syncthreads();
+        CTA_SYNC();
         if (tid == 0 && nb16) {
             mbar_expect_tx(&S.mbar, nb16);
             bulk_g2s(S.in, src, nb16, &S.mbar);
@@ -151,9 +168,9 @@ lz4_compress_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, ui
         for (uint32_t i = nb16 + tid; i < n; i += C_NT) S.in[i] = src[i];
         for (uint32_t i = n + tid; i < ((n + 3) & ~3u) + 32 && i < LZ4_BLK + 32; i += C_NT) S.in[i] = 0;
         for (uint32_t i = tid; i < (1u << C_HASHLOG); i += C_NT) S.tab[i] = 0;
-        if (nb16) mbar_wait(&S.mbar, 0);
-        __syncthreads();
-        if (tid == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&S.mbar)));
+        // one thread observes the TMA completion; the CTA barrier publishes the staged bytes to everyone
+        if (tid == 0 && nb16) { mbar_wait(&S.mbar, 0); asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&S.mbar))); }
+        CTA_SYNC();
 
         const uint32_t limit = n - 5;                     // matches end at or before n-5 (n >= 13 whenever a match exists)
         uint32_t e = 0, anchor = 0, out_pos = 0;          // CTA-uniform parse state
@@ -173,7 +190,12 @@ lz4_compress_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, ui
                     const uint32_t h = (v * 2654435761u) >> (32 - C_HASHLOG);
                     hreg[k] = ok ? h : 0xFFFFFFFFu;
                     uint32_t o = 0;
+#ifdef ZMT_DBG_NOMATCH
+                    uint32_t same = 0;
+                    for (int l = 0; l < 32; l++) { const uint32_t ov = __shfl_sync(ZMT_FULL_MASK, v, l); if (ov == v && (uint32_t)l < lane) same |= 1u << l; }
+#else
                     const uint32_t same = __match_any_sync(ZMT_FULL_MASK, v) & ((1u << lane) - 1);
+#endif
                     if (ok) {
                         if (same) o = lane - (31 - __clz(same));
                         else {
@@ -186,53 +208,67 @@ lz4_compress_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, ui
                     if (lane == 0) S.M[rel >> 5] = mw;
                     anyM |= mw;
                 }
-                __syncthreads();
+                CTA_SYNC();
 #pragma unroll
                 for (uint32_t k = 0; k < 4; k++)
                     if (hreg[k] != 0xFFFFFFFFu) atomicMax(&S.tab[hreg[k]], t0 + r * C_ROUND + k * C_NT + tid + 1);
-                __syncthreads();
+                CTA_SYNC();
             }
             const uint32_t t1 = t0 + C_TILE;
+#ifdef ZMT_DBG_NOOR
+            if (tid == 0) S.e_next = 0;
+            CTA_SYNC();
+            if (anyM && lane == 0) atomicOr(&S.e_next, 1u);
+            CTA_SYNC();
+            const int tile_has_match = S.e_next != 0;
+            CTA_SYNC();
+#else
+            __syncwarp();
             const int tile_has_match = __syncthreads_or(anyM != 0);
+#endif
             if (!tile_has_match || e >= t1) { if (e < t1) e = t1; continue; }   // nothing to parse in this tile
 
+            if (flags & 2) continue;
             // ---------------- phase 2: speculative chains (own segment, then continuation)
             const uint32_t k0 = (e - t0) / C_SEG;
             const uint32_t seg0 = t0 + tid * C_SEG;
             const bool alive = tid >= k0;
             if (alive) c_walk<0>(S, tid, tid == k0 ? e : seg0, t0, limit);
             else S.link[tid] = (uint16_t)tid;             // dead: self link, never reached
-            __syncthreads();
+            CTA_SYNC();
             if (alive) c_walk<1>(S, tid, S.xfree[tid], t0, limit);
-            __syncthreads();
+            CTA_SYNC();
+            if (flags & 4) continue;
             // ---------------- phase 3: reachability from k0 by pointer doubling
             {
                 uint32_t lk = S.link[tid];
                 S.jump[tid] = (uint16_t)(lk == C_END ? tid : lk);
                 S.reach[tid] = (tid == k0);
-                __syncthreads();
+                CTA_SYNC();
 #pragma unroll 1
                 for (int r = 0; r < 8; r++) {
                     const uint32_t j = S.jump[tid];
                     const uint32_t rk = S.reach[tid];
                     const uint32_t jj = S.jump[j];
-                    __syncthreads();
+                    CTA_SYNC();
                     if (rk) S.reach[j] = 1;
                     S.jump[tid] = (uint16_t)jj;
-                    __syncthreads();
+                    CTA_SYNC();
                 }
                 if (tid == k0) S.min_[tid] = e;
                 if (S.reach[tid]) {
                     if (lk == C_END) S.e_next = S.mpos[tid];
                     else S.min_[lk] = S.mpos[tid];
                 }
-                __syncthreads();
+                CTA_SYNC();
             }
+            if (flags & 8) continue;
             // ---------------- phase 4: mark the true chain
             if (S.reach[tid]) c_walk<2>(S, tid, S.min_[tid], t0, limit);
-            __syncthreads();
+            CTA_SYNC();
             e = S.e_next;
 
+            if (flags & 16) continue;
             // ---------------- phase 5: emit the selected sequences
             uint32_t nseq;
             {
@@ -240,8 +276,9 @@ lz4_compress_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, ui
                 uint32_t base = block_exscan(__popc(w), S.scanws, &nseq);
                 while (w) { uint32_t b = __ffs(w) - 1; w &= w - 1; S.seqpos[base++] = (uint16_t)(tid * 32 + b); }
             }
-            __syncthreads();
+            CTA_SYNC();
             if (nseq == 0) continue;
+            if (flags & 32) { const uint32_t lq = S.seqpos[nseq - 1]; anchor = t0 + lq + S.len[lq]; continue; }
             uint32_t lit4[4], len4[4], off4[4], pe4[4], sz = 0, cnt = 0;
 #pragma unroll
             for (uint32_t k = 0; k < 4; k++) {
@@ -270,7 +307,7 @@ lz4_compress_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, ui
                 if (ml >= 15) { uint32_t x = ml - 15; while (x >= 255) { *op++ = 255; x -= 255; } *op++ = (uint8_t)x; }
                 o += c_seq_size(lit, len4[k]);
             }
-            __syncthreads();
+            CTA_SYNC();
             {   // cooperative copies of long literal runs: one warp per run
                 const uint32_t nl = S.nlong;
                 for (uint32_t s = wid; s < nl; s += C_NT / 32) {
@@ -280,7 +317,7 @@ lz4_compress_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, ui
                 const uint32_t lastq = S.seqpos[nseq - 1];
                 anchor = t0 + lastq + S.len[lastq];
                 out_pos += total;
-                __syncthreads();
+                CTA_SYNC();
                 if (tid == 0) S.nlong = 0;
             }
         }
@@ -587,6 +624,18 @@ __global__ void lz4_verify_kernel(uint32_t* __restrict__ status, const uint32_t*
 }
 
 // ============================================================================ host launchers
+// ZSTDMT_B200_DEBUG_SYNC=1: synchronise after every kernel and name the one that failed (debug only)
+static bool zmt_dbg_check(cudaStream_t st, const char* what)
+{
+    static int on = -1;
+    if (on < 0) on = getenv("ZSTDMT_B200_DEBUG_SYNC") ? 1 : 0;
+    if (!on) return true;
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { fprintf(stderr, "[zstdmt_b200] %s failed: %s\n", what, cudaGetErrorString(e)); return false; }
+    return true;
+}
+
 static inline int zmt_sm_count()
 {
     static int n = 0;
@@ -637,15 +686,22 @@ extern "C" int zmt_lz4_compress_device(const void* d_in, uint64_t in_bytes, uint
     uint64_t* frame_size = (uint64_t*)w;
 
     cudaFuncSetAttribute(lz4_compress_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CompressSmem));
+    const unsigned dm = getenv("ZSTDMT_B200_DEBUG_MASK") ? (unsigned)atoi(getenv("ZSTDMT_B200_DEBUG_MASK")) : 31u;
     const uint32_t maxc = (uint32_t)(zmt_sm_count() * 2 * 8);
-    const uint32_t gridc = nblocks < maxc ? nblocks : maxc;
-    lz4_compress_blocks_kernel<<<gridc, C_NT, sizeof(CompressSmem), stream>>>((const uint8_t*)d_in, in_bytes, chunk_size, d_chunk_bytes, bpc, tmp, blk_csize, nblocks);
-    xxh32_kernel<<<(nchunks * 4 + 127) / 128, 128, 0, stream>>>((const uint8_t*)d_in, nullptr, nullptr, d_chunk_bytes, chunk_size, in_bytes, chk, nchunks);
-    lz4_frame_sizes_kernel<<<(nchunks + 255) / 256, 256, 0, stream>>>(blk_csize, in_bytes, chunk_size, d_chunk_bytes, bpc, nchunks, frame_size);
-    scan_u64_kernel<<<1, 1024, 0, stream>>>(frame_size, d_frame_off, nchunks);
+    uint32_t gridc = nblocks < maxc ? nblocks : maxc;
+    if (getenv("ZSTDMT_B200_DEBUG_GRID")) gridc = (uint32_t)atoi(getenv("ZSTDMT_B200_DEBUG_GRID"));
+    if (dm & 1) lz4_compress_blocks_kernel<<<gridc, C_NT, sizeof(CompressSmem), stream>>>((const uint8_t*)d_in, in_bytes, chunk_size, d_chunk_bytes, bpc, tmp, blk_csize, nblocks, (getenv("ZSTDMT_B200_NO_TMA") ? 1u : 0u) | (getenv("ZSTDMT_B200_DEBUG_FLAGS") ? (unsigned)atoi(getenv("ZSTDMT_B200_DEBUG_FLAGS")) : 0u));
+    zmt_dbg_check(stream, "lz4_compress_blocks_kernel");
+    if (dm & 2) xxh32_kernel<<<(nchunks * 4 + 127) / 128, 128, 0, stream>>>((const uint8_t*)d_in, nullptr, nullptr, d_chunk_bytes, chunk_size, in_bytes, chk, nchunks);
+    zmt_dbg_check(stream, "xxh32_kernel");
+    if (dm & 4) lz4_frame_sizes_kernel<<<(nchunks + 255) / 256, 256, 0, stream>>>(blk_csize, in_bytes, chunk_size, d_chunk_bytes, bpc, nchunks, frame_size);
+    zmt_dbg_check(stream, "lz4_frame_sizes_kernel");
+    if (dm & 8) scan_u64_kernel<<<1, 1024, 0, stream>>>(frame_size, d_frame_off, nchunks);
+    zmt_dbg_check(stream, "scan_u64_kernel");
     const uint32_t maxp = (uint32_t)(zmt_sm_count() * 16);
     const uint32_t gridp = nblocks < maxp ? nblocks : maxp;
-    lz4_frame_pack_kernel<<<gridp, 256, 0, stream>>>((const uint8_t*)d_in, in_bytes, chunk_size, d_chunk_bytes, bpc, tmp, blk_csize, chk, d_frame_off, (uint8_t*)d_out, nblocks);
+    if (dm & 16) lz4_frame_pack_kernel<<<gridp, 256, 0, stream>>>((const uint8_t*)d_in, in_bytes, chunk_size, d_chunk_bytes, bpc, tmp, blk_csize, chk, d_frame_off, (uint8_t*)d_out, nblocks);
+    zmt_dbg_check(stream, "lz4_frame_pack_kernel");
     return cudaGetLastError() == cudaSuccess ? ZMT_ST_OK : ZMT_ST_CUDA;
 }
 
