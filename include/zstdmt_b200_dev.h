@@ -53,13 +53,22 @@ uint64_t zmt_lz4c_out_bound(uint32_t nchunks, uint32_t chunk_size);
 int      zmt_lz4_compress_device(const void* d_in, uint64_t in_bytes, uint32_t chunk_size, const uint32_t* d_chunk_bytes,
                                  uint32_t nchunks, void* d_work, void* d_out, uint64_t* d_frame_off, void* stream);
 
-/* d_frame_off[f] = offset (in d_in) of frame f's 12-byte header, d_frame_csize[f] = its payload
- * size; d_out_off[f..f+1] = where frame f's content goes and how much room it has;
- * d_out_size[f] / d_status[f] receive decoded bytes and a ZMT_ST_* code. */
+/* d_in/in_bytes = the framed stream in HBM; d_frame_off[f] = offset of frame f's 12-byte header, d_frame_csize[f] =
+ * its payload size; d_out_off[f..f+1] = where frame f's content goes and how much room it has;
+ * max_blocks_per_frame = max over frames of ceil(room / 64 KiB) (warps launched per frame: frames with independent
+ * blocks are decoded one warp per block); d_out_size[f] / d_status[f] receive decoded bytes and a ZMT_ST_* code. */
 size_t   zmt_lz4d_workspace_bytes(uint32_t nframes);
-int      zmt_lz4_decompress_device(const void* d_in, const uint64_t* d_frame_off, const uint32_t* d_frame_csize, uint32_t nframes,
-                                   void* d_out, const uint64_t* d_out_off, uint64_t* d_out_size, uint32_t* d_status,
-                                   void* d_work, void* stream);
+int      zmt_lz4_decompress_device(const void* d_in, uint64_t in_bytes, const uint64_t* d_frame_off, const uint32_t* d_frame_csize, uint32_t nframes,
+                                   uint32_t max_blocks_per_frame, void* d_out, const uint64_t* d_out_off, uint64_t* d_out_size,
+                                   uint32_t* d_status, void* d_work, void* stream);
+
+/* ---- per-kernel device timing (CUDA events on the launching stream) ----
+ * zmt_prof_begin() arms it; every kernel launched by the entry points above is bracketed by two
+ * events; zmt_prof_end() (after the caller synchronised the stream) sums them per kernel id. */
+enum { ZMT_K_LZ4_COMPRESS = 0, ZMT_K_XXH32, ZMT_K_LZ4_SIZES, ZMT_K_SCAN, ZMT_K_LZ4_PACK, ZMT_K_LZ4_DECODE, ZMT_K_XXH32_DEC,
+       ZMT_K_ZSTD_COMPRESS, ZMT_K_ZSTD_PACK, ZMT_K_ZSTD_DECODE, ZMT_K_COUNT };
+void zmt_prof_begin(void);
+int  zmt_prof_end(double* ms, int* count, int max_ids);
 
 /* ---- synthetic inputs (csrc/datagen.c) ---- */
 void zmt_gen_chunk(int kind, uint64_t chunk_index, uint8_t* buf, size_t n);

@@ -103,15 +103,15 @@ long orc_lz4_block_decode(const uint8_t* src, size_t srcSize, uint8_t* dst, size
  *   eligible(i)  : i + 12 <= n                (LZ4 MFLIMIT: no match starts in the last 12 bytes)
  *   v(i)         : LE32 at i;  h(i) = (v * 2654435761) >> 20          (12-bit hash)
  *   rounds of 1024 positions; table[h] = 1 + max eligible position with hash h in EARLIER rounds
- *   local cand   : nearest j < i in the same 32-aligned window with v(j) == v(i)
+ *   local cand   : smallest d in 1..4 (d <= i) with v(i-d) == v(i)        (runs / short periods)
  *   table cand   : table[h(i)]-1 if v(cand) == v(i)
- *   off(i)       : i - local  else  i - table  else 0 (no match)
+ *   off(i)       : d  else  i - table  else 0 (no match)
  *   parse        : greedy — first match start >= p, length extended while
  *                  q+L < n-5 (LASTLITERALS); p = q + L
  */
 #define B200_HASHLOG 12
 #define B200_ROUND   1024
-#define B200_WINDOW  32
+#define B200_LOCAL   4
 
 size_t orc_lz4_block_bound(size_t n) { return n + n / 255 + 16; }
 
@@ -131,12 +131,11 @@ void orc_lz4_b200_offsets(const uint8_t* src, size_t n, uint16_t* off)
     for (r = 0; r < n; r += B200_ROUND) {
         size_t rend = r + B200_ROUND < n ? r + B200_ROUND : n;
         for (i = r; i < rend; i++) {
-            uint32_t v; size_t j, w0; int found = 0;
+            uint32_t v; size_t d; int found = 0;
             if (i + 12 > n) continue;
             v = rd32(src + i);
-            w0 = i & ~(size_t)(B200_WINDOW - 1);
-            for (j = i; j-- > w0;) {                      /* nearest lower lane with identical 4 bytes */
-                if (rd32(src + j) == v) { off[i] = (uint16_t)(i - j); found = 1; break; }
+            for (d = 1; d <= B200_LOCAL && d <= i; d++) {    /* short-period candidate: smallest d with identical 4 bytes */
+                if (rd32(src + i - d) == v) { off[i] = (uint16_t)d; found = 1; break; }
             }
             if (!found) {
                 uint32_t t = table[(v * 2654435761u) >> (32 - B200_HASHLOG)];
@@ -148,8 +147,6 @@ void orc_lz4_b200_offsets(const uint8_t* src, size_t n, uint16_t* off)
             table[(rd32(src + i) * 2654435761u) >> (32 - B200_HASHLOG)] = (uint32_t)i + 1;
         }
     }
-    /* note: position j in the local window that is itself not eligible can never be < an
-     * eligible i (eligibility is a prefix property), so no eligibility test on j is needed. */
     free(table);
 }
 

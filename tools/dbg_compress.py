@@ -15,5 +15,13 @@ torch.cuda.synchronize()
 f = out[: int(foff[-1])].cpu().numpy()
 e = o.orc_encode_lz4(src, 1 << 20)
 print("sizes", f.size, e.size, "equal", f.size == e.size and np.array_equal(f, e))
+if os.environ.get("TIME"):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(2): comp.run(d_in)
+    e0.record()
+    for _ in range(5): comp.run(d_in)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    print("ms/step %.3f  in GB/s %.1f  in+out GB/s %.1f" % (ms, n / ms / 1e6, (n + f.size) / ms / 1e6))
 if f.size == e.size and not np.array_equal(f, e):
     d = np.nonzero(f != e)[0]; print("first diff", d[:5])

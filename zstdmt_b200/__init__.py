@@ -64,7 +64,7 @@ def lib():
     L.zmt_lz4_compress_device.argtypes = [c_vp, c_u64, c_u32, c_vp, c_u32, c_vp, c_vp, c_vp, c_vp]
     L.zmt_lz4d_workspace_bytes.restype = c_sz; L.zmt_lz4d_workspace_bytes.argtypes = [c_u32]
     L.zmt_lz4_decompress_device.restype = ctypes.c_int
-    L.zmt_lz4_decompress_device.argtypes = [c_vp, c_vp, c_vp, c_u32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
+    L.zmt_lz4_decompress_device.argtypes = [c_vp, c_u64, c_vp, c_vp, c_u32, c_u32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
     for pre, api in (("LZ4MT", "lz4"), ("ZSTDCB", "zstd"), ("ZSTDMT", "zstd")):
         getattr(L, pre + "_createCCtx").restype = c_vp; getattr(L, pre + "_createCCtx").argtypes = [ctypes.c_int] * 3
         getattr(L, pre + "_createDCtx").restype = c_vp; getattr(L, pre + "_createDCtx").argtypes = [ctypes.c_int] * 2
@@ -173,6 +173,7 @@ class Lz4DeviceDecompressor:
         self.d_cs = torch.from_numpy(np.asarray(frame_csize, dtype=np.int32)).to(device)
         oo = np.zeros(self.n + 1, dtype=np.int64); oo[1:] = np.cumsum(np.asarray(out_sizes, dtype=np.int64))
         self.out_total = int(oo[-1])
+        self.max_bpf = int(max(1, max((int(x) + 65535) // 65536 for x in out_sizes))) if len(out_sizes) else 1
         self.d_out_off = torch.from_numpy(oo).to(device)
         self.out = torch.empty(max(self.out_total, 1), dtype=torch.uint8, device=device)
         self.out_size = torch.zeros(self.n, dtype=torch.int64, device=device)
@@ -182,8 +183,8 @@ class Lz4DeviceDecompressor:
     def run(self, d_framed, stream=None):
         torch = _torch()
         s = stream if stream is not None else torch.cuda.current_stream()
-        rc = lib().zmt_lz4_decompress_device(d_framed.data_ptr(), self.d_off.data_ptr(), self.d_cs.data_ptr(), self.n,
-                                             self.out.data_ptr(), self.d_out_off.data_ptr(), self.out_size.data_ptr(),
+        rc = lib().zmt_lz4_decompress_device(d_framed.data_ptr(), d_framed.numel(), self.d_off.data_ptr(), self.d_cs.data_ptr(), self.n,
+                                             self.max_bpf, self.out.data_ptr(), self.d_out_off.data_ptr(), self.out_size.data_ptr(),
                                              self.status.data_ptr(), self.work.data_ptr(), s.cuda_stream)
         if rc != 0:
             raise RuntimeError("zmt_lz4_decompress_device failed: %s" % ST_NAMES.get(rc, rc))

@@ -21,6 +21,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -32,7 +33,7 @@ size_t   zmt_zstdc_workspace_bytes(uint32_t nchunks, uint32_t chunk_size) __attr
 uint64_t zmt_zstdc_out_bound(uint32_t nchunks, uint32_t chunk_size) __attribute__((weak));
 int      zmt_zstd_compress_device(const void*, uint64_t, uint32_t, const uint32_t*, uint32_t, void*, void*, uint64_t*, void*) __attribute__((weak));
 size_t   zmt_zstdd_workspace_bytes(uint32_t nframes) __attribute__((weak));
-int      zmt_zstd_decompress_device(const void*, const uint64_t*, const uint32_t*, uint32_t, void*, const uint64_t*, uint64_t*, uint32_t*, void*, void*) __attribute__((weak));
+int      zmt_zstd_decompress_device(const void*, uint64_t, const uint64_t*, const uint32_t*, uint32_t, uint32_t, void*, const uint64_t*, uint64_t*, uint32_t*, void*, void*) __attribute__((weak));
 }
 
 namespace {
@@ -94,13 +95,20 @@ std::vector<int> env_devices()
     return devs;
 }
 
+// ------------------------------------------------------------------ optional stage timing (ZSTDMT_B200_TRACE=1)
+struct StageClock {
+    double cb = 0, wait = 0, gpu = 0;       // seconds: inside callbacks / waiting for a slot or queue / CUDA sync + copies
+    static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+};
+inline bool trace_on() { static int on = -1; if (on < 0) on = getenv("ZSTDMT_B200_TRACE") ? 1 : 0; return on == 1; }
+
 // ------------------------------------------------------------------ device codec table
 struct CodecOps {
     size_t   (*c_work)(uint32_t nchunks, uint32_t chunk);
     uint64_t (*c_bound)(uint32_t nchunks, uint32_t chunk);
     int      (*compress)(const void*, uint64_t, uint32_t, const uint32_t*, uint32_t, void*, void*, uint64_t*, void*);
     size_t   (*d_work)(uint32_t nframes);
-    int      (*decompress)(const void*, const uint64_t*, const uint32_t*, uint32_t, void*, const uint64_t*, uint64_t*, uint32_t*, void*, void*);
+    int      (*decompress)(const void*, uint64_t, const uint64_t*, const uint32_t*, uint32_t, uint32_t, void*, const uint64_t*, uint64_t*, uint32_t*, void*, void*);
 };
 
 
@@ -122,6 +130,7 @@ struct Slot {
     uint8_t *h_tab = nullptr, *d_tab = nullptr; size_t tab_bytes = 0;
     // batch contents
     uint32_t n = 0;              // chunks / frames in this batch
+    uint32_t max_bpf = 1;        // decompress: max 64 KiB blocks per frame in this batch
     size_t in_used = 0, out_used = 0;
     int state = 0;               // 0 free, 1 filled, 2 submitted
     bool ok = false;
@@ -135,7 +144,7 @@ inline Tables tables_at(uint8_t* base, size_t cap)
     Tables t; t.a = (uint64_t*)base; t.b = t.a + cap + 1; t.c = t.b + cap + 1; t.d = (uint32_t*)(t.c + cap + 1); t.e = t.d + cap; return t;
 }
 
-void slot_free(Slot& s)
+void slot_free_raw(Slot& s)
 {
     cudaSetDevice(s.dev);
     if (s.stream) cudaStreamSynchronize(s.stream);
@@ -151,7 +160,7 @@ void slot_free(Slot& s)
     s = Slot();
 }
 
-bool slot_alloc(Slot& s, int dev, size_t in_cap, size_t out_cap, size_t work_cap, size_t tab_cap)
+bool slot_alloc_raw(Slot& s, int dev, size_t in_cap, size_t out_cap, size_t work_cap, size_t tab_cap)
 {
     s.dev = dev;
     if (cudaSetDevice(dev) != cudaSuccess) return false;
@@ -167,8 +176,42 @@ bool slot_alloc(Slot& s, int dev, size_t in_cap, size_t out_cap, size_t work_cap
     ok = ok && cudaHostAlloc((void**)&s.h_tab, s.tab_bytes, cudaHostAllocPortable) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&s.d_tab, s.tab_bytes) == cudaSuccess;
     s.in_cap = in_cap; s.out_cap = out_cap; s.work_cap = work_cap; s.tab_cap = tab_cap; s.ok = ok;
-    if (!ok) { cudaGetLastError(); slot_free(s); }
+    if (!ok) { cudaGetLastError(); slot_free_raw(s); }
     return ok;
+}
+
+// Process-wide pool of staging slots: pinned allocations cost ~0.1 s per context otherwise (the reference's
+// malloc'd buffers are free by comparison).  Slots go back to the pool when a context is freed and are
+// reused by the next context that needs the same device and no larger capacities.
+std::mutex g_pool_mu;
+std::vector<Slot> g_pool;
+const size_t kPoolMax = 16;
+
+bool slot_alloc(Slot& s, int dev, size_t in_cap, size_t out_cap, size_t work_cap, size_t tab_cap)
+{
+    {
+        std::lock_guard<std::mutex> g(g_pool_mu);
+        for (size_t i = 0; i < g_pool.size(); i++) {
+            Slot& c = g_pool[i];
+            if (c.dev == dev && c.in_cap >= in_cap && c.out_cap >= out_cap && c.work_cap >= work_cap && c.tab_cap == tab_cap) {
+                s = c; g_pool.erase(g_pool.begin() + (long)i);
+                s.state = 0; s.n = 0; s.in_used = s.out_used = 0;
+                return true;
+            }
+        }
+    }
+    return slot_alloc_raw(s, dev, in_cap, out_cap, work_cap, tab_cap);
+}
+
+void slot_free(Slot& s)
+{
+    if (s.ok) {
+        cudaSetDevice(s.dev);
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        std::lock_guard<std::mutex> g(g_pool_mu);
+        if (g_pool.size() < kPoolMax && !getenv("ZSTDMT_B200_NO_POOL")) { g_pool.push_back(s); s = Slot(); return; }
+    }
+    slot_free_raw(s);
 }
 
 // ------------------------------------------------------------------ pipeline state shared by the 3 threads
@@ -203,13 +246,15 @@ size_t compress_run(Ctx* c, GenRdWr* rw)
     if (!ops->compress || !ops->c_work || !ops->c_bound) { c->lib_errcode = ZMT_ST_UNSUPPORTED; return E.library; }
     Pipe& P = c->pipe;
     const size_t chunk = c->inputsize;
-    size_t batch_bytes = env_size("ZSTDMT_B200_BATCH_MB", 64) << 20;
+    // small batches keep the pinned staging ring cache-resident, which is what the (serialised, memcpy-bound)
+    // fn_read / fn_write callbacks run against; 8 MiB measured best on the 2-socket Xeon hosts of the B200 pool
+    size_t batch_bytes = env_size("ZSTDMT_B200_BATCH_MB", 8) << 20;
     size_t B = batch_bytes / chunk; if (B < 1) B = 1; if (B > 65536) B = 65536;
 
     if (P.slots.empty()) {
         c->devs = env_devices();
         if (c->devs.empty()) { c->lib_errcode = ZMT_ST_CUDA; return E.library; }
-        int per_dev = c->threads >= 3 ? 3 : 2;
+        int per_dev = c->threads >= 4 ? 4 : c->threads >= 3 ? 3 : 2;
         P.slots.resize(c->devs.size() * per_dev);
         for (size_t i = 0; i < P.slots.size(); i++) {
             if (!slot_alloc(P.slots[i], c->devs[i % c->devs.size()], B * chunk, (size_t)ops->c_bound((uint32_t)B, (uint32_t)chunk),
@@ -221,21 +266,26 @@ size_t compress_run(Ctx* c, GenRdWr* rw)
     for (auto& s : P.slots) s.state = 0;
 
     // ---- reader: fills slots in sequence order (pt_compress read section, lz4-mt_compress.c:255-277)
+    StageClock ck_r, ck_w, ck_s;
     std::thread reader([&]() {
         size_t frames_read = 0; bool eof = false;
         while (!eof) {
             Slot* s;
             {
+                const double t0 = StageClock::now();
                 std::unique_lock<std::mutex> lk(P.mu);
                 s = &P.slots[P.fill_seq % N];
                 P.cv.wait(lk, [&] { return s->state == 0 || P.error; });
+                ck_r.wait += StageClock::now() - t0;
                 if (P.error) break;
             }
             Tables T = tables_at(s->h_tab, s->tab_cap);
             uint32_t n = 0; size_t got_bytes = 0;
             while (n < B) {
                 GenBuffer b; b.buf = s->h_in + (size_t)n * chunk; b.size = chunk; b.allocated = chunk;
+                const double t0 = StageClock::now();
                 int rv = rw->fn_read(rw->arg_read, &b);
+                ck_r.cb += StageClock::now() - t0;
                 if (rv != 0) { P.fail(mt_error(E, rv)); eof = true; n = 0; break; }
                 if (b.size > chunk) { P.fail(E.read_fail); eof = true; n = 0; break; }
                 if (b.size == 0 && frames_read > 0) { eof = true; break; }
@@ -259,25 +309,31 @@ size_t compress_run(Ctx* c, GenRdWr* rw)
         for (;;) {
             Slot* s;
             {
+                const double t0 = StageClock::now();
                 std::unique_lock<std::mutex> lk(P.mu);
                 s = &P.slots[P.write_seq % N];
                 P.cv.wait(lk, [&] { return s->state == 2 || P.error || (P.reader_done && P.write_seq == P.fill_seq); });
+                ck_w.wait += StageClock::now() - t0;
                 if (P.error || s->state != 2) break;
             }
             cudaSetDevice(s->dev);
+            const double tg = StageClock::now();
             if (cudaEventSynchronize(s->ev) != cudaSuccess) { c->lib_errcode = ZMT_ST_CUDA; P.fail(E.library); break; }
             Tables T = tables_at(s->h_tab, s->tab_cap);
             const uint64_t total = T.a[s->n];
             if (total > s->out_cap) { c->lib_errcode = ZMT_ST_DST_SMALL; P.fail(E.library); break; }
             if (cudaMemcpyAsync(s->h_out, s->d_out, total, cudaMemcpyDeviceToHost, s->stream) != cudaSuccess ||
                 cudaStreamSynchronize(s->stream) != cudaSuccess) { c->lib_errcode = ZMT_ST_CUDA; P.fail(E.library); break; }
+            ck_w.gpu += StageClock::now() - tg;
             bool bad = false;
+            const double tc = StageClock::now();
             for (uint32_t i = 0; i < s->n; i++) {
                 GenBuffer b; b.buf = s->h_out + T.a[i]; b.size = (size_t)(T.a[i + 1] - T.a[i]); b.allocated = b.size;
                 int rv = rw->fn_write(rw->arg_write, &b);
                 if (rv != 0) { P.fail(mt_error(E, rv)); bad = true; break; }
                 c->outsize += b.size; c->curframe++;
             }
+            ck_w.cb += StageClock::now() - tc;
             if (bad) break;
             { std::lock_guard<std::mutex> g(P.mu); s->state = 0; P.write_seq++; }
             P.cv.notify_all();
@@ -288,11 +344,14 @@ size_t compress_run(Ctx* c, GenRdWr* rw)
     for (;;) {
         Slot* s;
         {
+            const double t0 = StageClock::now();
             std::unique_lock<std::mutex> lk(P.mu);
             s = &P.slots[P.submit_seq % N];
             P.cv.wait(lk, [&] { return s->state == 1 || P.error || (P.reader_done && P.submit_seq == P.fill_seq); });
+            ck_s.wait += StageClock::now() - t0;
             if (P.error || s->state != 1) break;
         }
+        const double ts = StageClock::now();
         cudaSetDevice(s->dev);
         Tables Th = tables_at(s->h_tab, s->tab_cap), Td = tables_at(s->d_tab, s->tab_cap);
         bool full = true;
@@ -310,11 +369,15 @@ size_t compress_run(Ctx* c, GenRdWr* rw)
             if (ce != cudaSuccess) st = ZMT_ST_CUDA;
         }
         if (st != ZMT_ST_OK) { c->lib_errcode = (size_t)st; P.fail(E.library); break; }
+        ck_s.gpu += StageClock::now() - ts;
         { std::lock_guard<std::mutex> g(P.mu); s->state = 2; P.submit_seq++; }
         P.cv.notify_all();
     }
     reader.join(); writer.join();
     for (auto& s : P.slots) { cudaSetDevice(s.dev); cudaStreamSynchronize(s.stream); }
+    if (trace_on())
+        fprintf(stderr, "[zstdmt_b200] compress: reader cb %.3fs wait %.3fs | submit enqueue %.3fs wait %.3fs | writer gpu-wait %.3fs cb %.3fs wait %.3fs | slots %zu x %zu chunks\n",
+                ck_r.cb, ck_r.wait, ck_s.gpu, ck_s.wait, ck_w.gpu, ck_w.cb, ck_w.wait, N, B);
     return P.error;
 }
 
@@ -494,6 +557,7 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
             if (n == 0) break;
             T.b[n] = out_used;
             s->n = n; s->in_used = in_used; s->out_used = (size_t)out_used;
+            { uint64_t mx = 1; for (uint32_t i = 0; i < n; i++) { const uint64_t o = T.b[i + 1] - T.b[i]; const uint64_t nb = (o + 65535) / 65536; if (nb > mx) mx = nb; } s->max_bpf = (uint32_t)mx; }
             {
                 std::lock_guard<std::mutex> g(P.mu);
                 c->insize += stat_in; c->frames += n;
@@ -551,7 +615,7 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
         cudaError_t ce = cudaMemcpyAsync(s->d_in, s->h_in, s->in_used, cudaMemcpyHostToDevice, s->stream);
         if (ce == cudaSuccess) ce = cudaMemcpyAsync(s->d_tab, s->h_tab, s->tab_bytes, cudaMemcpyHostToDevice, s->stream);
         int st = ZMT_ST_CUDA;
-        if (ce == cudaSuccess) st = ops->decompress(s->d_in, Td.a, Td.d, s->n, s->d_out, Td.b, Td.c, Td.e, s->d_work, s->stream);
+        if (ce == cudaSuccess) st = ops->decompress(s->d_in, s->in_used, Td.a, Td.d, s->n, s->max_bpf, s->d_out, Td.b, Td.c, Td.e, s->d_work, s->stream);
         if (st == ZMT_ST_OK) {
             if (s->out_used) ce = cudaMemcpyAsync(s->h_out, s->d_out, s->out_used, cudaMemcpyDeviceToHost, s->stream);
             if (ce == cudaSuccess) ce = cudaMemcpyAsync(Th.c, Td.c, (size_t)s->n * 8, cudaMemcpyDeviceToHost, s->stream);

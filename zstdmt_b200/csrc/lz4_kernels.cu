@@ -19,6 +19,7 @@
 // oracle/lz4_oracle.c:orc_lz4_block_compress_b200 (tests compare bit-exact).
 #include <stdio.h>
 #include <stdlib.h>
+#include <vector>
 #include "common.cuh"
 #include "zmt_dev.h"
 
@@ -44,83 +45,107 @@ __device__ __forceinline__ uint64_t zmt_chunk_len(const uint32_t* __restrict__ c
 #define C_SEG        16u           // C_TILE / C_NT : positions owned by one speculative chain
 #define C_ROUND      1024u         // hash-table update granularity
 #define C_HASHLOG    12
-#define C_MAXSEQ     1024u         // max sequences per tile (min advance 4)
+#define C_MAXPIECE   1280u         // max pieces per tile: 4096/4 match pieces + 256 continuation pieces
 #define C_LONGLIT    32u           // literal runs longer than this are copied cooperatively
 #define C_END        0xFFFFu       // link: chain leaves the tile
 
 struct __align__(16) CompressSmem {
+    uint8_t  pad0[16];                    // bytes "before" the block (read by the 8-byte window of phase 1, never matched)
     uint8_t  in[LZ4_BLK + 32];            // block bytes + zero pad
     uint32_t tab[1 << C_HASHLOG];         // hash -> 1 + position
-    uint16_t off[C_TILE];                 // per tile position: match offset (0 = none)
-    uint16_t len[C_TILE];                 // per visited match start: match length
-    uint32_t M[C_TILE / 32];              // has-match bits
+    uint16_t off[C_TILE];                 // per tile position: candidate offset (0 = none)
+    uint8_t  len[C_TILE];                 // per piece start: piece length (<= 19)
+    uint32_t M[C_TILE / 32];              // has-candidate bits
     uint32_t V[C_TILE / 32];              // visited-by-own-chain bits
-    uint32_t Sel[C_TILE / 32];            // selected (true greedy chain) bits
-    uint32_t xfree[C_NT];                 // own-walk exit (free position, absolute)
+    uint32_t Sel[C_TILE / 32];            // pieces on the true greedy chain
+    uint32_t Cont[C_TILE / 32];           // ... that continue the previous piece's match across a segment boundary
+    uint32_t xfree[C_NT];                 // own-walk exit position (absolute)
+    uint16_t xdin[C_NT];                  // own-walk exit: offset of the match we are still inside (0 = free)
     uint32_t mpos[C_NT];                  // merge position / tile exit (absolute)
-    uint32_t min_[C_NT];                  // entry free position of a reachable chain
-    uint16_t link[C_NT];                  // chain this chain merges into (or C_END / dead)
+    uint32_t min_[C_NT];                  // entry (free) position of a reachable chain
+    uint16_t link[C_NT];                  // chain this chain merges into (C_END: leaves the tile)
     uint16_t jump[C_NT];
     uint8_t  reach[C_NT];
-    uint16_t seqpos[C_MAXSEQ];            // tile-relative start of the r-th selected sequence
-    uint32_t longl[3 * (C_TILE / C_LONGLIT + 1)];
+    uint16_t piece[C_MAXPIECE];           // tile-relative start of the r-th selected piece
+    uint16_t hidx[C_MAXPIECE];            // piece index of the h-th head
+    uint32_t longl[3 * (C_TILE / C_LONGLIT + 2)];
     uint32_t scanws[40];
     uint32_t nlong;
-    uint32_t e_next;                      // chain entry for the next tile
+    uint32_t e_next;                      // chain state entering the next tile: position ...
+    uint32_t d_next;                      // ... and offset of the match still open there (0 = free)
     uint64_t mbar;
 };
 
-__device__ __forceinline__ uint32_t c_match_len(const uint8_t* s, uint32_t q, uint32_t c, uint32_t limit)
+// number of bytes (<= cap) for which s[p + i] == s[p + i - d]
+__device__ __forceinline__ uint32_t c_extend(const uint8_t* s, uint32_t p, uint32_t d, uint32_t cap)
 {
-    uint32_t L = 4;
-    while (q + L + 4 <= limit) {
-        uint32_t x = lds32u(s, q + L) ^ lds32u(s, c + L);
+    uint32_t L = 0;
+    while (L + 4 <= cap) {
+        const uint32_t x = lds32u(s, p + L) ^ lds32u(s, p + L - d);
         if (x) return L + ((__ffs(x) - 1) >> 3);
         L += 4;
     }
-    while (q + L < limit && s[q + L] == s[c + L]) L++;
+    while (L < cap && s[p + L] == s[p + L - d]) L++;
     return L;
 }
 
-// Walk one speculative chain.  MODE 0: own segment only (sets V, caches len, returns exit in xfree)
-//                              MODE 1: continuation until merge/end (records link/mpos)
-//                              MODE 2: re-walk of a reachable chain (marks Sel) — same steps as 0+1.
+// Walk one speculative chain through the tile.  The greedy parse is evaluated piecewise: a match is cut at
+// the first segment boundary that leaves it >= 4 bytes, and continues ("inside", din = its offset) into the
+// next segment, so no lane ever compares more than 19 bytes per step.  Pieces are merged again at emission.
+//   MODE 0: own segment only (sets V, caches len, exit state -> xfree/xdin)
+//   MODE 1: continuation until it merges into another chain or leaves the tile (-> link/mpos)
+//   MODE 2: re-walk of a chain that is on the true path: marks Sel/Cont (same steps as MODE 0 + 1)
 template <int MODE>
-__device__ __forceinline__ void c_walk(CompressSmem& S, uint32_t k, uint32_t p, uint32_t t0, uint32_t limit)
+__device__ __forceinline__ void c_walk(CompressSmem& S, uint32_t k, uint32_t p, uint32_t din, uint32_t t0, uint32_t limit)
 {
-    // Single-exit loop (no returns from inside): divergent lanes leave through one reconvergence
-    // point, so the warp is whole again before the CTA barrier that follows every call.
     const uint32_t t1 = t0 + C_TILE;
-    uint32_t lk = 0xFFFFFFFFu, mp = 0;          // result: link / merge position (MODE 1), exit (MODE 0)
+    uint32_t lk = 0xFFFFFFFFu, mp = 0;
     bool done = false;
-    while (!done) {
+    while (!done) {                                  // single exit: the warp reconverges before the next barrier
         if (p >= t1) { lk = C_END; mp = p; done = true; continue; }
         const uint32_t rel = p - t0, j = rel / C_SEG;
         if (MODE == 0 && j != k) { mp = p; done = true; continue; }
+        if (din) {
+            // inside a match with offset din that covered everything up to the boundary p
+            if (MODE != 0 && j != k && ((S.M[rel >> 5] >> (rel & 31)) & 1) && S.off[rel] == din) {
+                lk = j; mp = p; done = true; continue;          // chain j's own first step is this very match
+            }
+            uint32_t cap = p < limit ? limit - p : 0; if (cap > C_SEG) cap = C_SEG;
+            const uint32_t E = c_extend(S.in, p, din, cap);
+            if (MODE == 2 && E) { atomicOr(&S.Sel[rel >> 5], 1u << (rel & 31)); atomicOr(&S.Cont[rel >> 5], 1u << (rel & 31)); S.len[rel] = (uint8_t)E; }
+            p += E;
+            if (E != C_SEG) din = 0;
+            continue;
+        }
         if (MODE != 0 && j != k && (rel & (C_SEG - 1)) == 0) { lk = j; mp = p; done = true; continue; }
-        uint32_t bits = (S.M[rel >> 5] >> (rel & 16)) & 0xFFFFu;     // this segment's 16 bits
+        uint32_t bits = (S.M[rel >> 5] >> (rel & 16)) & 0xFFFFu;     // this segment's 16 candidate bits
         bits &= 0xFFFFu << (rel & 15);
-        if (!bits) {                                                   // segment exhausted -> free position at its end
+        if (!bits) {                                                   // segment exhausted: free at its end
             const uint32_t nx = t0 + (j + 1) * C_SEG;
             if (MODE == 0) { mp = nx; done = true; }
             else if (j + 1 == C_NT) { lk = C_END; mp = t1; done = true; }
             else if (j != k) { lk = j + 1; mp = nx; done = true; }
-            else p = nx;                                               // MODE 2 inside own segment
+            else p = nx;
             continue;
         }
         const uint32_t qr = (rel & ~15u) + (__ffs(bits) - 1), q = t0 + qr;
         if (MODE != 0 && j != k && ((S.V[qr >> 5] >> (qr & 31)) & 1)) { lk = j; mp = q; done = true; continue; }
+        const uint32_t d = S.off[qr];
+        uint32_t B = (q & ~(C_SEG - 1)) + C_SEG;                     // cut at the first boundary leaving >= 4 bytes
+        if (B - q < 4) B += C_SEG;
         uint32_t L;
         if (MODE == 2) { atomicOr(&S.Sel[qr >> 5], 1u << (qr & 31)); L = S.len[qr]; }
         else {
-            L = c_match_len(S.in, q, q - S.off[qr], limit);
-            S.len[qr] = (uint16_t)L;
+            const uint32_t end = B < limit ? B : limit;
+            L = 4 + c_extend(S.in, q + 4, d, end - (q + 4));        // first 4 bytes are known equal; q + 4 <= limit always
+            S.len[qr] = (uint8_t)L;
             if (MODE == 0) atomicOr(&S.V[qr >> 5], 1u << (qr & 31));
         }
         p = q + L;
+        if (p == B) din = d;                                          // reached the boundary: still inside the match
     }
-    if (MODE == 0) S.xfree[k] = mp;
-    if (MODE == 1) { S.link[k] = (uint16_t)lk; S.mpos[k] = mp; }
+    if (MODE == 0) { S.xfree[k] = mp; S.xdin[k] = (uint16_t)din; }
+    if (MODE == 1) { S.link[k] = (uint16_t)lk; S.mpos[k] = mp; if (lk == C_END) S.xdin[k] = (uint16_t)din; }
 }
 
 __device__ __forceinline__ uint32_t c_seq_size(uint32_t lit, uint32_t L)
@@ -131,10 +156,23 @@ __device__ __forceinline__ uint32_t c_seq_size(uint32_t lit, uint32_t L)
     return s;
 }
 
-#ifndef ZMT_DBG_OCC
-#define ZMT_DBG_OCC 2
-#endif
-__global__ void __launch_bounds__(C_NT, ZMT_DBG_OCC)
+// writes one LZ4 sequence at op (token, lengths, offset); literals longer than C_LONGLIT are queued for a
+// warp-cooperative copy.  Returns the encoded size.
+__device__ __forceinline__ uint32_t c_emit_seq(CompressSmem& S, uint8_t* dst, uint32_t o, uint32_t lit_start, uint32_t lit, uint32_t off, uint32_t mlen)
+{
+    uint8_t* op = dst + o;
+    const uint32_t ml = mlen - 4;
+    *op++ = (uint8_t)(((lit >= 15 ? 15u : lit) << 4) | (ml >= 15 ? 15u : ml));
+    if (lit >= 15) { uint32_t x = lit - 15; while (x >= 255) { *op++ = 255; x -= 255; } *op++ = (uint8_t)x; }
+    if (lit <= C_LONGLIT) { for (uint32_t i = 0; i < lit; i++) op[i] = S.in[lit_start + i]; }
+    else { const uint32_t s = atomicAdd(&S.nlong, 1u); S.longl[3 * s] = lit_start; S.longl[3 * s + 1] = (uint32_t)(op - dst); S.longl[3 * s + 2] = lit; }
+    op += lit;
+    *op++ = (uint8_t)off; *op++ = (uint8_t)(off >> 8);
+    if (ml >= 15) { uint32_t x = ml - 15; while (x >= 255) { *op++ = 255; x -= 255; } *op++ = (uint8_t)x; }
+    return (uint32_t)(op - (dst + o));
+}
+
+__global__ void __launch_bounds__(C_NT, 2)
 lz4_compress_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32_t chunk_size, const uint32_t* __restrict__ chunk_bytes,
                            uint32_t bpc, uint8_t* __restrict__ tmp, uint32_t* __restrict__ blk_csize, uint32_t nblocks, uint32_t flags)
 {
@@ -154,30 +192,27 @@ lz4_compress_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, ui
         uint8_t* dst = tmp + (uint64_t)blk * ZMT_LZ4_TMP_STRIDE;
 
         // ---- stage the block into shared memory (TMA bulk copy when 16-byte aligned)
-        CTA_SYNC();                                  // previous block fully consumed
+        CTA_SYNC();                                       // previous block fully consumed
         const uint32_t nb16 = ((((uintptr_t)src & 15) == 0) && !(flags & 1)) ? (n & ~15u) : 0;
-        if (tid == 0) {
-            mbar_init(&S.mbar, 1);
-            S.nlong = 0;
-        }
+        if (tid == 0) { if (nb16) mbar_init(&S.mbar, 1); S.nlong = 0; }
         CTA_SYNC();
-        if (tid == 0 && nb16) {
-            mbar_expect_tx(&S.mbar, nb16);
-            bulk_g2s(S.in, src, nb16, &S.mbar);
-        }
+        if (tid == 0 && nb16) { mbar_expect_tx(&S.mbar, nb16); bulk_g2s(S.in, src, nb16, &S.mbar); }
         for (uint32_t i = nb16 + tid; i < n; i += C_NT) S.in[i] = src[i];
         for (uint32_t i = n + tid; i < ((n + 3) & ~3u) + 32 && i < LZ4_BLK + 32; i += C_NT) S.in[i] = 0;
+        if (tid < 16) S.pad0[tid] = 0;
         for (uint32_t i = tid; i < (1u << C_HASHLOG); i += C_NT) S.tab[i] = 0;
         // one thread observes the TMA completion; the CTA barrier publishes the staged bytes to everyone
         if (tid == 0 && nb16) { mbar_wait(&S.mbar, 0); asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&S.mbar))); }
         CTA_SYNC();
 
-        const uint32_t limit = n - 5;                     // matches end at or before n-5 (n >= 13 whenever a match exists)
-        uint32_t e = 0, anchor = 0, out_pos = 0;          // CTA-uniform parse state
+        const uint32_t limit = n >= 5 ? n - 5 : 0;        // matches end at or before n-5
+        uint32_t e = 0, e_din = 0, out_pos = 0;           // CTA-uniform parse state (position, offset of the open match)
+        // pending sequence: its match may still grow in the next tile, so it is emitted one tile late
+        uint32_t pd_valid = 0, pd_lit = 0, pd_start = 0, pd_off = 0, pd_end = 0;
 
         for (uint32_t t0 = 0; t0 < n; t0 += C_TILE) {
             // ---------------- phase 1: candidates (4 rounds of 1024 positions)
-            if (tid < C_TILE / 32) { S.V[tid] = 0; S.Sel[tid] = 0; }
+            if (tid < C_TILE / 32) { S.V[tid] = 0; S.Sel[tid] = 0; S.Cont[tid] = 0; }
             uint32_t anyM = 0;
 #pragma unroll 1
             for (uint32_t r = 0; r < C_TILE / C_ROUND; r++) {
@@ -186,18 +221,20 @@ lz4_compress_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, ui
                 for (uint32_t k = 0; k < 4; k++) {
                     const uint32_t rel = r * C_ROUND + k * C_NT + tid, i = t0 + rel;
                     const bool ok = (i + 12 <= n);
-                    const uint32_t v = lds32u(S.in, i);
+                    // 8-byte window: bytes i-4 .. i+3  (S.in is preceded by 16 pad bytes, so word -1 exists)
+                    const uint32_t* w = reinterpret_cast<const uint32_t*>(S.in) + (i >> 2);
+                    const uint32_t sh = (i & 3) * 8;
+                    const uint32_t w0 = w[-1], w1 = w[0], w2 = w[1];
+                    const uint32_t v = __funnelshift_r(w1, w2, sh), pv = __funnelshift_r(w0, w1, sh);
                     const uint32_t h = (v * 2654435761u) >> (32 - C_HASHLOG);
                     hreg[k] = ok ? h : 0xFFFFFFFFu;
                     uint32_t o = 0;
-#ifdef ZMT_DBG_NOMATCH
-                    uint32_t same = 0;
-                    for (int l = 0; l < 32; l++) { const uint32_t ov = __shfl_sync(ZMT_FULL_MASK, v, l); if (ov == v && (uint32_t)l < lane) same |= 1u << l; }
-#else
-                    const uint32_t same = __match_any_sync(ZMT_FULL_MASK, v) & ((1u << lane) - 1);
-#endif
                     if (ok) {
-                        if (same) o = lane - (31 - __clz(same));
+                        // short-period candidates d = 1..4: v(i-d) is a byte-shift of the window
+                        if (i >= 1 && __funnelshift_r(pv, v, 24) == v) o = 1;
+                        else if (i >= 2 && __funnelshift_r(pv, v, 16) == v) o = 2;
+                        else if (i >= 3 && __funnelshift_r(pv, v, 8) == v) o = 3;
+                        else if (i >= 4 && pv == v) o = 4;
                         else {
                             const uint32_t t = S.tab[h];
                             if (t && lds32u(S.in, t - 1) == v) o = i - (t - 1);
@@ -215,33 +252,22 @@ lz4_compress_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, ui
                 CTA_SYNC();
             }
             const uint32_t t1 = t0 + C_TILE;
-#ifdef ZMT_DBG_NOOR
-            if (tid == 0) S.e_next = 0;
-            CTA_SYNC();
-            if (anyM && lane == 0) atomicOr(&S.e_next, 1u);
-            CTA_SYNC();
-            const int tile_has_match = S.e_next != 0;
-            CTA_SYNC();
-#else
             __syncwarp();
             const int tile_has_match = __syncthreads_or(anyM != 0);
-#endif
-            if (!tile_has_match || e >= t1) { if (e < t1) e = t1; continue; }   // nothing to parse in this tile
+            if ((!tile_has_match && !e_din) || e >= t1) { if (e < t1) e = t1; continue; }   // nothing to parse in this tile
 
-            if (flags & 2) continue;
             // ---------------- phase 2: speculative chains (own segment, then continuation)
             const uint32_t k0 = (e - t0) / C_SEG;
             const uint32_t seg0 = t0 + tid * C_SEG;
             const bool alive = tid >= k0;
-            if (alive) c_walk<0>(S, tid, tid == k0 ? e : seg0, t0, limit);
+            if (alive) c_walk<0>(S, tid, tid == k0 ? e : seg0, tid == k0 ? e_din : 0u, t0, limit);
             else S.link[tid] = (uint16_t)tid;             // dead: self link, never reached
             CTA_SYNC();
-            if (alive) c_walk<1>(S, tid, S.xfree[tid], t0, limit);
+            if (alive) c_walk<1>(S, tid, S.xfree[tid], S.xdin[tid], t0, limit);
             CTA_SYNC();
-            if (flags & 4) continue;
             // ---------------- phase 3: reachability from k0 by pointer doubling
             {
-                uint32_t lk = S.link[tid];
+                const uint32_t lk = S.link[tid];
                 S.jump[tid] = (uint16_t)(lk == C_END ? tid : lk);
                 S.reach[tid] = (tid == k0);
                 CTA_SYNC();
@@ -257,38 +283,79 @@ lz4_compress_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, ui
                 }
                 if (tid == k0) S.min_[tid] = e;
                 if (S.reach[tid]) {
-                    if (lk == C_END) S.e_next = S.mpos[tid];
+                    if (lk == C_END) { S.e_next = S.mpos[tid]; S.d_next = S.xdin[tid]; }
                     else S.min_[lk] = S.mpos[tid];
                 }
                 CTA_SYNC();
             }
-            if (flags & 8) continue;
-            // ---------------- phase 4: mark the true chain
-            if (S.reach[tid]) c_walk<2>(S, tid, S.min_[tid], t0, limit);
+            // ---------------- phase 4: mark the pieces of the true chain
+            if (S.reach[tid]) c_walk<2>(S, tid, S.min_[tid], tid == k0 ? e_din : 0u, t0, limit);
             CTA_SYNC();
-            e = S.e_next;
+            e = S.e_next; e_din = S.d_next;
 
-            if (flags & 16) continue;
-            // ---------------- phase 5: emit the selected sequences
-            uint32_t nseq;
+            // ---------------- phase 5: merge pieces into sequences, emit all but the last (it may still grow)
+            uint32_t np;
             {
                 uint32_t w = tid < C_TILE / 32 ? S.Sel[tid] : 0;
-                uint32_t base = block_exscan(__popc(w), S.scanws, &nseq);
-                while (w) { uint32_t b = __ffs(w) - 1; w &= w - 1; S.seqpos[base++] = (uint16_t)(tid * 32 + b); }
+                uint32_t base = block_exscan(__popc(w), S.scanws, &np);
+                while (w) { const uint32_t b = __ffs(w) - 1; w &= w - 1; S.piece[base++] = (uint16_t)(tid * 32 + b); }
             }
             CTA_SYNC();
-            if (nseq == 0) continue;
-            if (flags & 32) { const uint32_t lq = S.seqpos[nseq - 1]; anchor = t0 + lq + S.len[lq]; continue; }
-            uint32_t lit4[4], len4[4], off4[4], pe4[4], sz = 0, cnt = 0;
+            if (np == 0) continue;
+            // piece r is a HEAD unless it continues the previous piece's match: flagged continuation, or contiguous with the
+            // same offset (the effective offset of a flagged piece is that of the nearest unflagged piece before it)
+            uint32_t nh_local = 0, headmask = 0;
+            constexpr uint32_t PPT = C_MAXPIECE / C_NT;   // pieces per thread
+#pragma unroll
+            for (uint32_t k = 0; k < PPT; k++) {
+                const uint32_t r = tid * PPT + k;
+                if (r < np) {
+                    const uint32_t pr = S.piece[r];
+                    bool head = !((S.Cont[pr >> 5] >> (pr & 31)) & 1);
+                    if (head) {
+                        uint32_t pend, poff;                         // end and effective offset of what precedes piece r
+                        if (r == 0) { pend = pd_valid ? pd_end : 0xFFFFFFFFu; poff = pd_off; }
+                        else {
+                            uint32_t b = r - 1, pb = S.piece[b];
+                            pend = t0 + pb + S.len[pb];
+                            while (((S.Cont[pb >> 5] >> (pb & 31)) & 1) && b > 0) { b--; pb = S.piece[b]; }
+                            poff = ((S.Cont[pb >> 5] >> (pb & 31)) & 1) ? pd_off : S.off[pb];
+                        }
+                        if (pend == t0 + pr && poff == S.off[pr]) head = false;
+                    }
+                    if (head) { headmask |= 1u << k; nh_local++; }
+                }
+            }
+            uint32_t nh;
+            {
+                uint32_t hb = block_exscan(nh_local, S.scanws, &nh);
+#pragma unroll
+                for (uint32_t k = 0; k < PPT; k++) if (headmask & (1u << k)) S.hidx[hb++] = (uint16_t)(tid * PPT + k);
+            }
+            CTA_SYNC();
+            const uint32_t lastp = S.piece[np - 1];
+            const uint32_t tile_end = t0 + lastp + S.len[lastp];     // end of the last piece of this tile
+            if (nh == 0) { pd_end = tile_end; continue; }            // every piece extends the pending sequence
+            if (pd_valid && S.hidx[0] > 0) { const uint32_t pb = S.piece[S.hidx[0] - 1]; pd_end = t0 + pb + S.len[pb]; }
+            // sequences to emit now: [pending] + heads 0 .. nh-2 ; head nh-1 becomes the new pending sequence
+            const uint32_t nemit = pd_valid + nh - 1;
+            uint32_t sz = 0, e_lit0[4], e_lit[4], e_off[4], e_len[4], cnt = 0;
 #pragma unroll
             for (uint32_t k = 0; k < 4; k++) {
-                const uint32_t r = tid * 4 + k;
-                if (r < nseq) {
-                    const uint32_t qr = S.seqpos[r];
-                    uint32_t pe = anchor;
-                    if (r) { const uint32_t pr = S.seqpos[r - 1]; pe = t0 + pr + S.len[pr]; }
-                    pe4[k] = pe; lit4[k] = t0 + qr - pe; len4[k] = S.len[qr]; off4[k] = S.off[qr];
-                    sz += c_seq_size(lit4[k], len4[k]); cnt++;
+                const uint32_t sidx = tid * 4 + k;
+                if (sidx < nemit) {
+                    uint32_t ls, st, of, en;
+                    if (pd_valid && sidx == 0) { ls = pd_lit; st = pd_start; of = pd_off; en = pd_end; }
+                    else {
+                        const uint32_t h = sidx - pd_valid;          // head index, h <= nh-2
+                        const uint32_t pi = S.hidx[h], pr = S.piece[pi];
+                        const uint32_t pl = S.piece[S.hidx[h + 1] - 1];
+                        st = t0 + pr; of = S.off[pr]; en = t0 + pl + S.len[pl];
+                        if (h == 0) ls = pd_valid ? pd_end : pd_lit;     // pd_lit doubles as "end of everything emitted so far"
+                        else { const uint32_t pp = S.piece[pi - 1]; ls = t0 + pp + S.len[pp]; }
+                    }
+                    e_lit0[k] = ls; e_lit[k] = st - ls; e_off[k] = of; e_len[k] = en - st;
+                    sz += c_seq_size(e_lit[k], e_len[k]); cnt++;
                 }
             }
             uint32_t total;
@@ -296,16 +363,7 @@ lz4_compress_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, ui
 #pragma unroll
             for (uint32_t k = 0; k < 4; k++) {
                 if (k >= cnt) break;
-                uint8_t* op = dst + o;
-                const uint32_t lit = lit4[k], ml = len4[k] - 4;
-                *op++ = (uint8_t)(((lit >= 15 ? 15u : lit) << 4) | (ml >= 15 ? 15u : ml));
-                if (lit >= 15) { uint32_t x = lit - 15; while (x >= 255) { *op++ = 255; x -= 255; } *op++ = (uint8_t)x; }
-                if (lit <= C_LONGLIT) { for (uint32_t i = 0; i < lit; i++) op[i] = S.in[pe4[k] + i]; }
-                else { const uint32_t s = atomicAdd(&S.nlong, 1u); S.longl[3 * s] = pe4[k]; S.longl[3 * s + 1] = (uint32_t)(op - dst); S.longl[3 * s + 2] = lit; }
-                op += lit;
-                *op++ = (uint8_t)off4[k]; *op++ = (uint8_t)(off4[k] >> 8);
-                if (ml >= 15) { uint32_t x = ml - 15; while (x >= 255) { *op++ = 255; x -= 255; } *op++ = (uint8_t)x; }
-                o += c_seq_size(lit, len4[k]);
+                o += c_emit_seq(S, dst, o, e_lit0[k], e_lit[k], e_off[k], e_len[k]);
             }
             CTA_SYNC();
             {   // cooperative copies of long literal runs: one warp per run
@@ -314,16 +372,31 @@ lz4_compress_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, ui
                     const uint32_t sp = S.longl[3 * s], dp = S.longl[3 * s + 1], ln = S.longl[3 * s + 2];
                     for (uint32_t i = lane; i < ln; i += 32) dst[dp + i] = S.in[sp + i];
                 }
-                const uint32_t lastq = S.seqpos[nseq - 1];
-                anchor = t0 + lastq + S.len[lastq];
                 out_pos += total;
+                // new pending = last head of this tile
+                const uint32_t pi = S.hidx[nh - 1], pr = S.piece[pi];
+                uint32_t ls;
+                if (nh >= 2 || pd_valid) { if (pi > 0) { const uint32_t pp = S.piece[pi - 1]; ls = t0 + pp + S.len[pp]; } else ls = pd_end; }
+                else ls = pd_lit;                          // first sequence of the block: literals start where emission stands (0)
+                pd_valid = 1; pd_lit = ls; pd_start = t0 + pr; pd_off = S.off[pr]; pd_end = tile_end;
                 CTA_SYNC();
                 if (tid == 0) S.nlong = 0;
             }
         }
 
-        // ---------------- last literals
+        // ---------------- flush the pending sequence + last literals
         {
+            uint32_t anchor = 0;
+            if (pd_valid) {
+                anchor = pd_end;
+                if (tid == 0) (void)c_emit_seq(S, dst, out_pos, pd_lit, pd_start - pd_lit, pd_off, pd_end - pd_start);
+                out_pos += c_seq_size(pd_start - pd_lit, pd_end - pd_start);
+                CTA_SYNC();
+                if (S.nlong) {                              // its literal run was long: copy it with the whole CTA
+                    const uint32_t sp = S.longl[0], dp = S.longl[1], ln = S.longl[2];
+                    for (uint32_t i = tid; i < ln; i += C_NT) dst[dp + i] = S.in[sp + i];
+                }
+            }
             const uint32_t lit = n - anchor;
             const uint32_t fin = out_pos + 1 + lit + (lit >= 15 ? 1 + (lit - 15) / 255 : 0);
             if (fin >= n) { if (tid == 0) blk_csize[blk] = n | 0x80000000u; }   // stored block (LZ4F rule)
@@ -344,39 +417,57 @@ lz4_compress_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, ui
 }
 
 // ============================================================================ XXH32 (content checksum)
-// 4 consecutive lanes own the 4 accumulators of one buffer; 8 buffers per warp.
-__global__ void __launch_bounds__(128)
+// One warp per buffer.  XXH32 is four serial accumulator chains (one per 32-bit word of every 16-byte
+// stripe), so the latency floor per buffer is (len/16) * ~12 cycles; everything else is about keeping the
+// four chain lanes fed: all 32 lanes stream the buffer with 16-byte loads (X_DEPTH tiles of 512 B in flight
+// per warp), park each tile in a per-warp shared-memory slot, and lanes 0..3 walk the slot word by word.
+#define X_WARPS 8
+#define X_DEPTH 4
+__global__ void __launch_bounds__(32 * X_WARPS)
 xxh32_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__ offs, const uint64_t* __restrict__ lens,
              const uint32_t* __restrict__ lens32, uint64_t stride, uint64_t total_bytes, uint32_t* __restrict__ out, uint32_t nbuf)
 {
-    const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 2, j = threadIdx.x & 3, lane = threadIdx.x & 31;
-    const bool live = g < nbuf;
-    uint64_t off = 0, n = 0;
-    if (live) {
-        if (offs) { off = offs[g]; n = lens ? lens[g] : offs[g + 1] - off; }
-        else { off = (uint64_t)g * stride; n = zmt_chunk_len(lens32, g, total_bytes, (uint32_t)stride); }
-    }
+    __shared__ uint4 tile[X_WARPS][2][32];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t g = blockIdx.x * X_WARPS + wid;
+    if (g >= nbuf) return;                                   // whole warp leaves together
+    uint64_t off, n;
+    if (offs) { off = offs[g]; n = lens ? lens[g] : offs[g + 1] - off; }
+    else { off = (uint64_t)g * stride; n = zmt_chunk_len(lens32, g, total_bytes, (uint32_t)stride); }
     const uint8_t* p = base + off;
+    const uint32_t j = lane & 3;
     uint32_t acc = j == 0 ? XXP1 + XXP2 : j == 1 ? XXP2 : j == 2 ? 0u : 0u - XXP1;
-    const uint64_t ns = n >> 4;
-    if (((uintptr_t)p & 3) == 0) {
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(p) + j;
-        uint64_t s = 0;
-        for (; s + 8 <= ns; s += 8) {
-            uint32_t x[8];
+    const uint64_t ns = n >> 4;                              // 16-byte stripes
+    uint64_t s = 0;
+    if (((uintptr_t)p & 15) == 0) {
+        const uint4* v = reinterpret_cast<const uint4*>(p);
+        const uint64_t nt = ns >> 5;                         // full tiles of 32 stripes
+        uint4 r[X_DEPTH];
 #pragma unroll
-            for (int u = 0; u < 8; u++) x[u] = __ldg(w + 4 * (s + u));
+        for (int d = 0; d < X_DEPTH; d++) if ((uint64_t)d < nt) r[d] = __ldg(v + (uint64_t)d * 32 + lane);
+        for (uint64_t t = 0; t < nt; t += X_DEPTH) {
 #pragma unroll
-            for (int u = 0; u < 8; u++) acc = xxh32_round(acc, x[u]);
+            for (int d = 0; d < X_DEPTH; d++) {
+                if (t + d < nt) {
+                    uint4* slot = tile[wid][d & 1];
+                    slot[lane] = r[d];
+                    if (t + d + X_DEPTH < nt) r[d] = __ldg(v + (t + d + X_DEPTH) * 32 + lane);
+                    __syncwarp();
+                    const uint32_t* w = reinterpret_cast<const uint32_t*>(slot) + j;
+#pragma unroll
+                    for (int q = 0; q < 32; q++) acc = xxh32_round(acc, w[4 * q]);
+                    __syncwarp();
+                }
+            }
         }
-        for (; s < ns; s++) acc = xxh32_round(acc, __ldg(w + 4 * s));
-    } else {
-        for (uint64_t s = 0; s < ns; s++) acc = xxh32_round(acc, ldg_le32(p + 16 * s + 4 * j));
+        s = nt << 5;
     }
-    const uint32_t gl = lane & ~3u;
-    const uint32_t a1 = __shfl_sync(ZMT_FULL_MASK, acc, gl), a2 = __shfl_sync(ZMT_FULL_MASK, acc, gl + 1);
-    const uint32_t a3 = __shfl_sync(ZMT_FULL_MASK, acc, gl + 2), a4 = __shfl_sync(ZMT_FULL_MASK, acc, gl + 3);
-    if (live && j == 0) {
+    // remaining stripes (and unaligned buffers): the 4 chain lanes read global memory directly
+    if (((uintptr_t)p & 3) == 0) { const uint32_t* w = reinterpret_cast<const uint32_t*>(p) + j; for (; s < ns; s++) acc = xxh32_round(acc, __ldg(w + 4 * s)); }
+    else for (; s < ns; s++) acc = xxh32_round(acc, ldg_le32(p + 16 * s + 4 * j));
+    const uint32_t a1 = __shfl_sync(ZMT_FULL_MASK, acc, 0), a2 = __shfl_sync(ZMT_FULL_MASK, acc, 1);
+    const uint32_t a3 = __shfl_sync(ZMT_FULL_MASK, acc, 2), a4 = __shfl_sync(ZMT_FULL_MASK, acc, 3);
+    if (lane == 0) {
         uint32_t h = n >= 16 ? rotl32(a1, 1) + rotl32(a2, 7) + rotl32(a3, 12) + rotl32(a4, 18) : XXP5;
         h += (uint32_t)n;
         const uint8_t* q = p + (ns << 4);
@@ -482,11 +573,37 @@ lz4_frame_pack_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32_
 }
 
 // ============================================================================ decoder
-// One warp per frame; all lanes parse the token stream in lockstep (uniform control flow),
-// copies are spread over the 32 lanes.  Handles linked and independent blocks, stored
-// blocks, block checksums (skipped), content size + content checksum (checked by the
-// follow-up xxh32_kernel + lz4_verify_kernel).
-#define D_WARPS 4
+// Work unit = one warp.  Frames with independent blocks (FLG.indep, what our encoder emits) get one warp per
+// 64 KiB block; frames with linked blocks (what liblz4 emits for the reference, lz4-mt_compress.c:141-146)
+// are decoded block after block by the frame's first warp, because a block may copy from the previous one.
+// The warp parses the sequence stream in lockstep (uniform control flow) out of a 1 KiB shared-memory window
+// that all 32 lanes refill with 16-byte loads, and spreads every literal / match copy over its lanes.
+#define D_WARPS 8
+#define D_WIN   1024u
+
+struct DWin { uint8_t* w; const uint8_t* gsrc; const uint8_t* in_end; int32_t pos; };   // pos: block-relative offset of w[0]
+
+__device__ __forceinline__ void dwin_fill(DWin& W, uint32_t ip, uint32_t lane)
+{
+    const int32_t np = (int32_t)ip - (int32_t)((uintptr_t)(W.gsrc + ip) & 15);
+    __syncwarp();
+#pragma unroll
+    for (uint32_t k = 0; k < D_WIN / 512; k++) {
+        const uint8_t* a = W.gsrc + np + (int32_t)(16 * (lane + 32 * k));
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (a + 16 <= W.in_end) v = *reinterpret_cast<const uint4*>(a);
+        else { uint8_t* b = reinterpret_cast<uint8_t*>(&v); for (int i = 0; i < 16; i++) if (a + i < W.in_end) b[i] = a[i]; }
+        reinterpret_cast<uint4*>(W.w)[lane + 32 * k] = v;
+    }
+    W.pos = np;
+    __syncwarp();
+}
+// make bytes [ip, ip + k) of the block available in the window (k <= D_WIN - 16)
+__device__ __forceinline__ void dwin_need(DWin& W, uint32_t ip, uint32_t k, uint32_t lane)
+{
+    if ((int32_t)ip < W.pos || (int32_t)(ip + k) > W.pos + (int32_t)D_WIN) dwin_fill(W, ip, lane);
+}
+__device__ __forceinline__ uint32_t dwin_byte(const DWin& W, uint32_t ip) { return W.w[(int32_t)ip - W.pos]; }
 
 __device__ __forceinline__ void warp_copy_lit(uint8_t* dst, const uint8_t* src, uint32_t n, uint32_t lane)
 {
@@ -505,31 +622,38 @@ __device__ __forceinline__ void warp_copy_lit(uint8_t* dst, const uint8_t* src, 
 }
 
 // returns decoded size or 0xFFFFFFFF on error.  `hist` = bytes of valid history before dst.
-__device__ uint32_t warp_decode_block(const uint8_t* __restrict__ src, uint32_t srcSize, uint8_t* dst, uint32_t dstCap,
-                                      uint64_t hist, uint32_t lane)
+__device__ uint32_t warp_decode_block(DWin& W, uint32_t srcSize, uint8_t* dst, uint32_t dstCap, uint64_t hist, uint32_t lane)
 {
     uint32_t ip = 0, op = 0;
     if (srcSize == 0) return 0xFFFFFFFFu;
     for (;;) {
         if (ip >= srcSize) return 0xFFFFFFFFu;
-        const uint32_t token = src[ip++];
+        dwin_need(W, ip, 20, lane);                         // token + a few length bytes + short literals' head
+        const uint32_t token = dwin_byte(W, ip++);
         uint32_t lit = token >> 4;
         if (lit == 15) {
             uint32_t b;
-            do { if (ip >= srcSize) return 0xFFFFFFFFu; b = src[ip++]; lit += b; } while (b == 255);
+            do { if (ip >= srcSize) return 0xFFFFFFFFu; dwin_need(W, ip, 1, lane); b = dwin_byte(W, ip++); lit += b; } while (b == 255);
         }
         if (lit > srcSize - ip || lit > dstCap - op) return 0xFFFFFFFFu;
-        warp_copy_lit(dst + op, src + ip, lit, lane);
+        if (lit) {
+            if (lit <= 256) {                               // short run: out of the window
+                dwin_need(W, ip, lit, lane);
+                const uint8_t* s = W.w + ((int32_t)ip - W.pos);
+                for (uint32_t i = lane; i < lit; i += 32) dst[op + i] = s[i];
+            } else warp_copy_lit(dst + op, W.gsrc + ip, lit, lane);
+        }
         ip += lit; op += lit;
         if (ip == srcSize) break;
         if (srcSize - ip < 2) return 0xFFFFFFFFu;
-        const uint32_t off = (uint32_t)src[ip] | ((uint32_t)src[ip + 1] << 8);
+        dwin_need(W, ip, 3, lane);
+        const uint32_t off = dwin_byte(W, ip) | (dwin_byte(W, ip + 1) << 8);
         ip += 2;
         if (off == 0 || (uint64_t)off > (uint64_t)op + hist) return 0xFFFFFFFFu;
         uint32_t ml = token & 15;
         if (ml == 15) {
             uint32_t b;
-            do { if (ip >= srcSize) return 0xFFFFFFFFu; b = src[ip++]; ml += b; } while (b == 255);
+            do { if (ip >= srcSize) return 0xFFFFFFFFu; dwin_need(W, ip, 1, lane); b = dwin_byte(W, ip++); ml += b; } while (b == 255);
         }
         ml += 4;
         if (ml > dstCap - op) return 0xFFFFFFFFu;
@@ -548,83 +672,145 @@ __device__ uint32_t warp_decode_block(const uint8_t* __restrict__ src, uint32_t 
     return op;
 }
 
-__global__ void __launch_bounds__(32 * D_WARPS)
-lz4_decode_frames_kernel(const uint8_t* __restrict__ in, const uint64_t* __restrict__ frame_off, const uint32_t* __restrict__ frame_csize,
-                         uint8_t* __restrict__ out, const uint64_t* __restrict__ out_off, uint64_t* __restrict__ out_size,
-                         uint32_t* __restrict__ status, uint32_t* __restrict__ stored_chk, uint32_t nframes)
+__device__ __forceinline__ void d_fail(uint32_t* status, uint32_t f, uint32_t code, uint32_t lane)
 {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t f = blockIdx.x * D_WARPS + (threadIdx.x >> 5);
+    if (lane == 0) atomicCAS(&status[f], 0u, code);        // first error wins
+}
+
+// status[] and out_size[] must be zero on entry (the launcher clears them).
+__global__ void __launch_bounds__(32 * D_WARPS)
+lz4_decode_frames_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ in_end, const uint64_t* __restrict__ frame_off,
+                         const uint32_t* __restrict__ frame_csize, uint8_t* __restrict__ out, const uint64_t* __restrict__ out_off,
+                         unsigned long long* __restrict__ out_size, uint32_t* __restrict__ status, uint32_t* __restrict__ stored_chk,
+                         uint32_t nframes, uint32_t max_bpf)
+{
+    __shared__ __align__(16) uint8_t win[D_WARPS][D_WIN];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint64_t gw = (uint64_t)blockIdx.x * D_WARPS + wid;
+    const uint32_t f = (uint32_t)(gw / max_bpf), slot = (uint32_t)(gw % max_bpf);
     if (f >= nframes) return;
     const uint8_t* p = in + frame_off[f] + 12;              // LZ4F frame (after the skippable header)
     const uint32_t fs = frame_csize[f];
     uint8_t* dst = out + out_off[f];
     const uint64_t cap = out_off[f + 1] - out_off[f];
-    uint32_t st = ZMT_ST_OK, has_chk = 0, chkv = 0;
-    uint64_t total = 0;
-    do {
-        if (fs < 7 + 4) { st = ZMT_ST_TRUNCATED; break; }
-        if (ldg_le32(p) != 0x184D2204u) { st = ZMT_ST_BAD_MAGIC; break; }
-        const uint32_t flg = p[4], bd = p[5];
-        if ((flg >> 6) != 1 || (flg & 2) || (bd & 0x8F) || ((bd >> 4) & 7) < 4) { st = ZMT_ST_BAD_HEADER; break; }
-        const uint32_t indep = (flg >> 5) & 1, bchk = (flg >> 4) & 1, csz = (flg >> 3) & 1, cchk = (flg >> 2) & 1, did = flg & 1;
-        const uint32_t blkmax = 1u << (8 + 2 * ((bd >> 4) & 7));
-        const uint32_t hl = 2 + (csz ? 8 : 0) + (did ? 4 : 0);
-        if (fs < 4 + hl + 1 + 4) { st = ZMT_ST_TRUNCATED; break; }
-        {
-            uint8_t h[14];
-            for (uint32_t i = 0; i < hl; i++) h[i] = p[4 + i];
-            if (((xxh32_small(h, hl, 0) >> 8) & 0xFF) != p[4 + hl]) { st = ZMT_ST_HDR_CHECKSUM; break; }
+    // ---- frame header (every warp of the frame re-reads it; only slot 0 reports header errors)
+    if (fs < 7 + 4) { if (slot == 0) d_fail(status, f, ZMT_ST_TRUNCATED, lane); return; }
+    if (ldg_le32(p) != 0x184D2204u) { if (slot == 0) d_fail(status, f, ZMT_ST_BAD_MAGIC, lane); return; }
+    const uint32_t flg = p[4], bd = p[5];
+    if ((flg >> 6) != 1 || (flg & 2) || (bd & 0x8F) || ((bd >> 4) & 7) < 4) { if (slot == 0) d_fail(status, f, ZMT_ST_BAD_HEADER, lane); return; }
+    const uint32_t indep = (flg >> 5) & 1, bchk = (flg >> 4) & 1, csz = (flg >> 3) & 1, cchk = (flg >> 2) & 1, did = flg & 1;
+    const uint32_t blkmax = 1u << (8 + 2 * ((bd >> 4) & 7));
+    const uint32_t hl = 2 + (csz ? 8 : 0) + (did ? 4 : 0);
+    if (fs < 4 + hl + 1 + 4) { if (slot == 0) d_fail(status, f, ZMT_ST_TRUNCATED, lane); return; }
+    if (slot == 0) {
+        uint8_t h[14];
+        for (uint32_t i = 0; i < hl; i++) h[i] = p[4 + i];
+        if (((xxh32_small(h, hl, 0) >> 8) & 0xFF) != p[4 + hl]) { d_fail(status, f, ZMT_ST_HDR_CHECKSUM, lane); return; }
+    }
+    if (!indep && slot != 0) return;                        // linked blocks: the frame's first warp does them all in order
+
+    DWin W; W.w = win[wid]; W.in_end = in_end;
+    uint32_t ip = 4 + hl + 1, b = 0;
+    uint64_t total = 0;                                     // output offset of the current block inside the frame
+    bool mine_done = false;
+    for (;;) {
+        if (fs - ip < 4) { d_fail(status, f, ZMT_ST_TRUNCATED, lane); return; }
+        const uint32_t bh = ldg_le32(p + ip);
+        if (bh == 0) {                                      // end mark
+            if (!indep || mine_done || b == 0) break;       // the warp that decoded the last block (or slot 0 of an empty frame) does the trailer
+            return;                                         // this slot is past the last block
         }
-        const uint64_t content = csz ? ldg_le64(p + 6) : 0;
-        uint32_t ip = 4 + hl + 1;
-        for (;;) {
-            if (fs - ip < 4) { st = ZMT_ST_TRUNCATED; break; }
-            const uint32_t bh = ldg_le32(p + ip); ip += 4;
-            if (bh == 0) break;
-            const uint32_t bs = bh & 0x7FFFFFFFu;
-            if (bs > blkmax) { st = ZMT_ST_BLOCK; break; }
-            if (fs - ip < bs + (bchk ? 4 : 0)) { st = ZMT_ST_TRUNCATED; break; }
-            if (bh & 0x80000000u) {
-                if (bs > cap - total) { st = ZMT_ST_DST_SMALL; break; }
-                __syncwarp();
-                warp_copy_lit(dst + total, p + ip, bs, lane);
-                total += bs;
-            } else {
-                const uint64_t room = cap - total;
-                const uint32_t dcap = room < blkmax ? (uint32_t)room : blkmax;
-                const uint64_t hist = indep ? 0 : (total < 65536 ? total : 65536);
-                const uint32_t d = warp_decode_block(p + ip, bs, dst + total, dcap, hist, lane);
-                if (d == 0xFFFFFFFFu) { st = ZMT_ST_BLOCK; break; }
-                total += d;
+        if (indep && mine_done) {                           // another block follows mine: its own warp handles it ...
+            if (slot + 1 == max_bpf) d_fail(status, f, ZMT_ST_BLOCK, lane);   // ... unless there is none: more blocks than slots
+            return;
+        }
+        ip += 4;
+        const uint32_t bs = bh & 0x7FFFFFFFu;
+        if (bs > blkmax) { d_fail(status, f, ZMT_ST_BLOCK, lane); return; }
+        if (fs - ip < bs + (bchk ? 4 : 0)) { d_fail(status, f, ZMT_ST_TRUNCATED, lane); return; }
+        if (indep && b != slot) { ip += bs + (bchk ? 4 : 0); b++; total += blkmax; continue; }   // not my block: skip over it
+        if (total > cap) { d_fail(status, f, ZMT_ST_DST_SMALL, lane); return; }
+        uint32_t d;
+        if (bh & 0x80000000u) {
+            if (bs > cap - total) { d_fail(status, f, ZMT_ST_DST_SMALL, lane); return; }
+            warp_copy_lit(dst + total, p + ip, bs, lane);
+            d = bs;
+        } else {
+            const uint64_t room = cap - total;
+            const uint32_t dcap = room < blkmax ? (uint32_t)room : blkmax;
+            const uint64_t hist = indep ? 0 : (total < 65536 ? total : 65536);
+            W.gsrc = p + ip; W.pos = 0x40000000;            // empty window
+            d = warp_decode_block(W, bs, dst + total, dcap, hist, lane);
+            if (d == 0xFFFFFFFFu) { d_fail(status, f, ZMT_ST_BLOCK, lane); return; }
+        }
+        if (lane == 0) atomicAdd(&out_size[f], (unsigned long long)d);
+        ip += bs + (bchk ? 4 : 0);
+        if (indep) {
+            // one-warp-per-block addressing assumes every block but the last regenerates exactly blkmax bytes
+            // (true for liblz4 and for our encoder); anything else is reported, not guessed
+            mine_done = true;
+            if (d != blkmax) {
+                if (fs - ip < 4) { d_fail(status, f, ZMT_ST_TRUNCATED, lane); return; }
+                if (ldg_le32(p + ip) != 0) { d_fail(status, f, ZMT_ST_BLOCK, lane); return; }
             }
-            ip += bs + (bchk ? 4 : 0);
-            __syncwarp();
         }
-        if (st != ZMT_ST_OK) break;
-        if (cchk) {
-            if (fs - ip < 4) { st = ZMT_ST_TRUNCATED; break; }
-            has_chk = 1; chkv = ldg_le32(p + ip); ip += 4;
-        }
-        if (csz && content != total) { st = ZMT_ST_CONTENT_SIZE; break; }
-        if (ip != fs) { st = ZMT_ST_TRAILING; break; }
-    } while (0);
-    if (lane == 0) { status[f] = st | (has_chk ? ZMT_ST_HAS_CHK : 0); stored_chk[f] = chkv; out_size[f] = total; }
+        total += d; b++;
+        __syncwarp();
+    }
+    // ---- trailer: end mark, optional content checksum, nothing after it
+    ip += 4;
+    uint32_t has_chk = 0, chkv = 0;
+    if (cchk) {
+        if (fs - ip < 4) { d_fail(status, f, ZMT_ST_TRUNCATED, lane); return; }
+        has_chk = 1; chkv = ldg_le32(p + ip); ip += 4;
+    }
+    if (ip != fs) { d_fail(status, f, ZMT_ST_TRAILING, lane); return; }
+    if (lane == 0) { stored_chk[f] = chkv; if (has_chk) atomicOr(&status[f], ZMT_ST_HAS_CHK); }
 }
 
-// compares xxh32 of the decoded output with the stored content checksum
-__global__ void lz4_verify_kernel(uint32_t* __restrict__ status, const uint32_t* __restrict__ stored_chk,
-                                  const uint32_t* __restrict__ computed, uint32_t nframes)
+// content-size check + comparison of the recomputed XXH32 with the stored content checksum
+__global__ void lz4_verify_kernel(const uint8_t* __restrict__ in, const uint64_t* __restrict__ frame_off, const uint32_t* __restrict__ frame_csize,
+                                  uint32_t* __restrict__ status, const unsigned long long* __restrict__ out_size,
+                                  const uint32_t* __restrict__ stored_chk, const uint32_t* __restrict__ computed, uint32_t nframes)
 {
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nframes) return;
     uint32_t st = status[f];
-    if ((st & ZMT_ST_HAS_CHK) && (st & 0xFF) == ZMT_ST_OK && stored_chk[f] != computed[f]) st = (st & ~0xFFu) | ZMT_ST_CONTENT_CHECKSUM;
+    if ((st & 0xFF) == ZMT_ST_OK) {
+        const uint8_t* p = in + frame_off[f] + 12;
+        if (frame_csize[f] >= 15 && (p[4] & 0x08) && ldg_le64(p + 6) != out_size[f]) st = ZMT_ST_CONTENT_SIZE;
+        else if ((st & ZMT_ST_HAS_CHK) && stored_chk[f] != computed[f]) st = ZMT_ST_CONTENT_CHECKSUM;
+    }
     status[f] = st & 0xFF;
 }
 
 // ============================================================================ host launchers
 // ZSTDMT_B200_DEBUG_SYNC=1: synchronise after every kernel and name the one that failed (debug only)
+// ---- optional per-kernel timing (zmt_prof_begin / zmt_prof_end): CUDA events recorded on the launching
+// stream around every kernel while enabled; used by bench.py for the roofline of the dominant kernel.
+struct ZmtProfRec { int id; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ZmtProfRec> g_prof;
+struct ZmtProfScope {
+    cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr; int id;
+    ZmtProfScope(int id_, cudaStream_t s) : st(s), id(id_) { if (g_prof_on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); } }
+    ~ZmtProfScope() { if (a) { cudaEventRecord(b, st); g_prof.push_back({id, a, b}); } }
+};
+extern "C" void zmt_prof_begin(void) { for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); } g_prof.clear(); g_prof_on = true; }
+// ms[id] = summed device time, count[id] = launches (the caller synchronises the stream first)
+extern "C" int zmt_prof_end(double* ms, int* count, int max_ids)
+{
+    g_prof_on = false;
+    for (int i = 0; i < max_ids; i++) { ms[i] = 0; count[i] = 0; }
+    for (auto& r : g_prof) {
+        float t = 0; cudaEventSynchronize(r.b);
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess && r.id < max_ids) { ms[r.id] += t; count[r.id]++; }
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    g_prof.clear();
+    return ZMT_K_COUNT < max_ids ? ZMT_K_COUNT : max_ids;
+}
+
 static bool zmt_dbg_check(cudaStream_t st, const char* what)
 {
     static int on = -1;
@@ -686,21 +872,24 @@ extern "C" int zmt_lz4_compress_device(const void* d_in, uint64_t in_bytes, uint
     uint64_t* frame_size = (uint64_t*)w;
 
     cudaFuncSetAttribute(lz4_compress_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CompressSmem));
-    const unsigned dm = getenv("ZSTDMT_B200_DEBUG_MASK") ? (unsigned)atoi(getenv("ZSTDMT_B200_DEBUG_MASK")) : 31u;
     const uint32_t maxc = (uint32_t)(zmt_sm_count() * 2 * 8);
     uint32_t gridc = nblocks < maxc ? nblocks : maxc;
-    if (getenv("ZSTDMT_B200_DEBUG_GRID")) gridc = (uint32_t)atoi(getenv("ZSTDMT_B200_DEBUG_GRID"));
-    if (dm & 1) lz4_compress_blocks_kernel<<<gridc, C_NT, sizeof(CompressSmem), stream>>>((const uint8_t*)d_in, in_bytes, chunk_size, d_chunk_bytes, bpc, tmp, blk_csize, nblocks, (getenv("ZSTDMT_B200_NO_TMA") ? 1u : 0u) | (getenv("ZSTDMT_B200_DEBUG_FLAGS") ? (unsigned)atoi(getenv("ZSTDMT_B200_DEBUG_FLAGS")) : 0u));
+    { ZmtProfScope ps(ZMT_K_LZ4_COMPRESS, stream);
+    lz4_compress_blocks_kernel<<<gridc, C_NT, sizeof(CompressSmem), stream>>>((const uint8_t*)d_in, in_bytes, chunk_size, d_chunk_bytes, bpc, tmp, blk_csize, nblocks, getenv("ZSTDMT_B200_NO_TMA") ? 1u : 0u); }
     zmt_dbg_check(stream, "lz4_compress_blocks_kernel");
-    if (dm & 2) xxh32_kernel<<<(nchunks * 4 + 127) / 128, 128, 0, stream>>>((const uint8_t*)d_in, nullptr, nullptr, d_chunk_bytes, chunk_size, in_bytes, chk, nchunks);
+    { ZmtProfScope ps(ZMT_K_XXH32, stream);
+    xxh32_kernel<<<(nchunks + X_WARPS - 1) / X_WARPS, 32 * X_WARPS, 0, stream>>>((const uint8_t*)d_in, nullptr, nullptr, d_chunk_bytes, chunk_size, in_bytes, chk, nchunks); }
     zmt_dbg_check(stream, "xxh32_kernel");
-    if (dm & 4) lz4_frame_sizes_kernel<<<(nchunks + 255) / 256, 256, 0, stream>>>(blk_csize, in_bytes, chunk_size, d_chunk_bytes, bpc, nchunks, frame_size);
+    { ZmtProfScope ps(ZMT_K_LZ4_SIZES, stream);
+    lz4_frame_sizes_kernel<<<(nchunks + 255) / 256, 256, 0, stream>>>(blk_csize, in_bytes, chunk_size, d_chunk_bytes, bpc, nchunks, frame_size); }
     zmt_dbg_check(stream, "lz4_frame_sizes_kernel");
-    if (dm & 8) scan_u64_kernel<<<1, 1024, 0, stream>>>(frame_size, d_frame_off, nchunks);
+    { ZmtProfScope ps(ZMT_K_SCAN, stream);
+    scan_u64_kernel<<<1, 1024, 0, stream>>>(frame_size, d_frame_off, nchunks); }
     zmt_dbg_check(stream, "scan_u64_kernel");
     const uint32_t maxp = (uint32_t)(zmt_sm_count() * 16);
     const uint32_t gridp = nblocks < maxp ? nblocks : maxp;
-    if (dm & 16) lz4_frame_pack_kernel<<<gridp, 256, 0, stream>>>((const uint8_t*)d_in, in_bytes, chunk_size, d_chunk_bytes, bpc, tmp, blk_csize, chk, d_frame_off, (uint8_t*)d_out, nblocks);
+    { ZmtProfScope ps(ZMT_K_LZ4_PACK, stream);
+    lz4_frame_pack_kernel<<<gridp, 256, 0, stream>>>((const uint8_t*)d_in, in_bytes, chunk_size, d_chunk_bytes, bpc, tmp, blk_csize, chk, d_frame_off, (uint8_t*)d_out, nblocks); }
     zmt_dbg_check(stream, "lz4_frame_pack_kernel");
     return cudaGetLastError() == cudaSuccess ? ZMT_ST_OK : ZMT_ST_CUDA;
 }
@@ -710,18 +899,28 @@ extern "C" size_t zmt_lz4d_workspace_bytes(uint32_t nframes)
     return (size_t)((((uint64_t)nframes * 4 + 255) & ~255ull) * 2 + 1024);
 }
 
-extern "C" int zmt_lz4_decompress_device(const void* d_in, const uint64_t* d_frame_off, const uint32_t* d_frame_csize, uint32_t nframes,
-                                         void* d_out, const uint64_t* d_out_off, uint64_t* d_out_size, uint32_t* d_status,
-                                         void* d_work, void* stream_)
+extern "C" int zmt_lz4_decompress_device(const void* d_in, uint64_t in_bytes, const uint64_t* d_frame_off, const uint32_t* d_frame_csize, uint32_t nframes,
+                                         uint32_t max_blocks_per_frame, void* d_out, const uint64_t* d_out_off, uint64_t* d_out_size,
+                                         uint32_t* d_status, void* d_work, void* stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (nframes == 0) return ZMT_ST_OK;
+    if (max_blocks_per_frame == 0) max_blocks_per_frame = 1;
     uint8_t* w = (uint8_t*)d_work;
     uint32_t* stored = (uint32_t*)w; w += (((uint64_t)nframes * 4 + 255) & ~255ull);
     uint32_t* computed = (uint32_t*)w;
-    lz4_decode_frames_kernel<<<(nframes + D_WARPS - 1) / D_WARPS, 32 * D_WARPS, 0, stream>>>((const uint8_t*)d_in, d_frame_off, d_frame_csize,
-                                                                                   (uint8_t*)d_out, d_out_off, d_out_size, d_status, stored, nframes);
-    xxh32_kernel<<<(nframes * 4 + 127) / 128, 128, 0, stream>>>((const uint8_t*)d_out, d_out_off, d_out_size, nullptr, 0, 0, computed, nframes);
-    lz4_verify_kernel<<<(nframes + 255) / 256, 256, 0, stream>>>(d_status, stored, computed, nframes);
+    cudaMemsetAsync(d_status, 0, (size_t)nframes * 4, stream);
+    cudaMemsetAsync(d_out_size, 0, (size_t)nframes * 8, stream);
+    cudaMemsetAsync(stored, 0, (size_t)nframes * 4, stream);
+    const uint64_t nwarps = (uint64_t)nframes * max_blocks_per_frame;
+    if ((nwarps + D_WARPS - 1) / D_WARPS > 0x7FFFFFFFull) return ZMT_ST_BAD_ARG;
+    { ZmtProfScope ps(ZMT_K_LZ4_DECODE, stream);
+    lz4_decode_frames_kernel<<<(uint32_t)((nwarps + D_WARPS - 1) / D_WARPS), 32 * D_WARPS, 0, stream>>>(
+        (const uint8_t*)d_in, (const uint8_t*)d_in + in_bytes, d_frame_off, d_frame_csize, (uint8_t*)d_out, d_out_off,
+        (unsigned long long*)d_out_size, d_status, stored, nframes, max_blocks_per_frame); }
+    { ZmtProfScope ps(ZMT_K_XXH32_DEC, stream);
+    xxh32_kernel<<<(nframes + X_WARPS - 1) / X_WARPS, 32 * X_WARPS, 0, stream>>>((const uint8_t*)d_out, d_out_off, d_out_size, nullptr, 0, 0, computed, nframes); }
+    lz4_verify_kernel<<<(nframes + 255) / 256, 256, 0, stream>>>((const uint8_t*)d_in, d_frame_off, d_frame_csize, d_status,
+                                                                (const unsigned long long*)d_out_size, stored, computed, nframes);
     return cudaGetLastError() == cudaSuccess ? ZMT_ST_OK : ZMT_ST_CUDA;
 }
