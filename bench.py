@@ -270,6 +270,22 @@ def run_b200(args):
     assert outb == framed
     # spot-check the e2e bytes against the device-path bytes
     assert np.array_equal(h_out[: 1 << 20], out[: 1 << 20].cpu().numpy())
+    if not args.no_extra:
+        # decompress end to end through LZ4MT_decompressDCtx (host buffers), on the stream just produced
+        back = np.empty(n + 16, np.uint8)
+        def d_step():
+            rc = L.zmt_lz4_decompress_mem(threads, 0, h_out.ctypes.data, outb, back.ctypes.data, n + 16, st)
+            assert rc == 0 and int(st[0]) == n, (rc, int(st[0]))
+        d_step()
+        barrier()
+        t = time.perf_counter()
+        for _ in range(args.steps):
+            d_step()
+        barrier()
+        d_s = allreduce(time.perf_counter() - t, dist.ReduceOp.MAX if world > 1 else None)
+        extra["lz4_decompress_e2e_gbs"] = e2e_alg * args.steps / d_s / 1e9
+        assert np.array_equal(back[: 1 << 22], src[: 1 << 22]) and np.array_equal(back[n - (1 << 20): n], src[n - (1 << 20):])
+        del back
 
     line = {
         "metric": "lz4-mt level-1 compress throughput, bytes in + framed bytes out", "value": value, "unit": "GB/s",
@@ -316,6 +332,16 @@ def run_b200(args):
                 # reference ratio on the sample (re-run value kept from the T=N run)
                 rc = o.ref().ref_lz4_compress_mem(T, 1, chunk, src.ctypes.data, ns, outr.ctypes.data, capr, str_)
                 line["cpu_baseline"]["ratio"] = ns / int(str_[0])
+                if not args.no_extra:
+                    # the reference decoding its own stream (T=nproc), same sample
+                    fr = outr[: int(str_[0])].copy(); backr = np.empty(ns + 16, np.uint8); bestd = None
+                    for _ in range(3):
+                        tt = time.perf_counter()
+                        rc = o.ref().ref_lz4_decompress_mem(T, 0, fr.ctypes.data, fr.size, backr.ctypes.data, ns + 16, str_)
+                        dt = time.perf_counter() - tt
+                        assert rc == 0
+                        bestd = dt if bestd is None else min(bestd, dt)
+                    line["cpu_baseline"]["lz4_decompress_gbs"] = (ns + fr.size) / bestd / 1e9
                 line["cpu_baseline"]["cpu_model"] = cpu_model()
             else:
                 line["cpu_baseline"] = {"value": None, "unit": "GB/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}

@@ -432,7 +432,8 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
     const CodecOps* ops = codec_ops(c->codec);
     if (!ops->decompress || !ops->d_work) { c->lib_errcode = ZMT_ST_UNSUPPORTED; return E.library; }
     Pipe& P = c->pipe;
-    const size_t in_cap0 = (env_size("ZSTDMT_B200_BATCH_MB", 64) << 20), out_cap0 = in_cap0 * 2, tab_cap = 8192;
+    // decode batches must hold enough frames to fill the GPU (one warp per 64 KiB block): 32 MiB of frames measured best
+    const size_t in_cap0 = (env_size("ZSTDMT_B200_DBATCH_MB", 32) << 20), out_cap0 = in_cap0 * 2, tab_cap = 8192;
 
     // ---- stream-type sniffing on the calling thread (LZ4MT_decompressDCtx, lz4-mt_decompress.c:503-520;
     //      ZSTDCB_decompressDCtx, zstd-mt_decompress.c:721-759)
@@ -473,7 +474,7 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
     if (P.slots.empty()) {
         c->devs = env_devices();
         if (c->devs.empty()) { c->lib_errcode = ZMT_ST_CUDA; return E.library; }
-        int per_dev = c->threads >= 3 ? 3 : 2;
+        int per_dev = c->threads >= 4 ? 4 : c->threads >= 3 ? 3 : 2;
         P.slots.resize(c->devs.size() * per_dev);
         for (size_t i = 0; i < P.slots.size(); i++)
             if (!slot_alloc(P.slots[i], c->devs[i % c->devs.size()], in_cap0, out_cap0, ops->d_work((uint32_t)tab_cap), tab_cap)) { ctx_release_slots(c); return E.mem; }
