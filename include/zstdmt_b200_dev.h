@@ -62,6 +62,13 @@ int      zmt_lz4_decompress_device(const void* d_in, uint64_t in_bytes, const ui
                                    uint32_t max_blocks_per_frame, void* d_out, const uint64_t* d_out_off, uint64_t* d_out_size,
                                    uint32_t* d_status, void* d_work, void* stream);
 
+/* ---- Zstandard ----  same layout contract as the LZ4 entry points; frames are single-segment zstd frames
+ * (magic, FHD, content size, blocks, no checksum) behind the same 12-byte container header. */
+size_t   zmt_zstdc_workspace_bytes(uint32_t nchunks, uint32_t chunk_size);
+uint64_t zmt_zstdc_out_bound(uint32_t nchunks, uint32_t chunk_size);
+int      zmt_zstd_compress_device(const void* d_in, uint64_t in_bytes, uint32_t chunk_size, const uint32_t* d_chunk_bytes,
+                                  uint32_t nchunks, void* d_work, void* d_out, uint64_t* d_frame_off, void* stream);
+
 /* ---- per-kernel device timing (CUDA events on the launching stream) ----
  * zmt_prof_begin() arms it; every kernel launched by the entry points above is bracketed by two
  * events; zmt_prof_end() (after the caller synchronised the stream) sums them per kernel id. */

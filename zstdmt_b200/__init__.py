@@ -62,6 +62,10 @@ def lib():
     L.zmt_lz4c_out_bound.restype = c_u64; L.zmt_lz4c_out_bound.argtypes = [c_u32, c_u32]
     L.zmt_lz4_compress_device.restype = ctypes.c_int
     L.zmt_lz4_compress_device.argtypes = [c_vp, c_u64, c_u32, c_vp, c_u32, c_vp, c_vp, c_vp, c_vp]
+    L.zmt_zstdc_workspace_bytes.restype = c_sz; L.zmt_zstdc_workspace_bytes.argtypes = [c_u32, c_u32]
+    L.zmt_zstdc_out_bound.restype = c_u64; L.zmt_zstdc_out_bound.argtypes = [c_u32, c_u32]
+    L.zmt_zstd_compress_device.restype = ctypes.c_int
+    L.zmt_zstd_compress_device.argtypes = [c_vp, c_u64, c_u32, c_vp, c_u32, c_vp, c_vp, c_vp, c_vp]
     L.zmt_lz4d_workspace_bytes.restype = c_sz; L.zmt_lz4d_workspace_bytes.argtypes = [c_u32]
     L.zmt_lz4_decompress_device.restype = ctypes.c_int
     L.zmt_lz4_decompress_device.argtypes = [c_vp, c_u64, c_vp, c_vp, c_u32, c_u32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
@@ -160,6 +164,27 @@ class Lz4DeviceCompressor:
                                            self.work.data_ptr(), self.out.data_ptr(), self.frame_off.data_ptr(), s.cuda_stream)
         if rc != 0:
             raise RuntimeError("zmt_lz4_compress_device failed: %s" % ST_NAMES.get(rc, rc))
+        return self.out, self.frame_off
+
+
+class ZstdDeviceCompressor:
+    """zmt_zstd_compress_device: same layout contract as the LZ4 twin, Zstandard frames out."""
+
+    def __init__(self, in_bytes, chunk, device="cuda"):
+        torch = _torch(); L = lib()
+        self.chunk, self.in_bytes = chunk, in_bytes
+        self.nchunks = L.zmt_chunk_count(in_bytes, chunk)
+        self.work = torch.empty(L.zmt_zstdc_workspace_bytes(self.nchunks, chunk), dtype=torch.uint8, device=device)
+        self.out = torch.empty(L.zmt_zstdc_out_bound(self.nchunks, chunk), dtype=torch.uint8, device=device)
+        self.frame_off = torch.zeros(self.nchunks + 1, dtype=torch.int64, device=device)
+
+    def run(self, d_in, stream=None):
+        torch = _torch()
+        s = stream if stream is not None else torch.cuda.current_stream()
+        rc = lib().zmt_zstd_compress_device(d_in.data_ptr(), self.in_bytes, self.chunk, None, self.nchunks,
+                                            self.work.data_ptr(), self.out.data_ptr(), self.frame_off.data_ptr(), s.cuda_stream)
+        if rc != 0:
+            raise RuntimeError("zmt_zstd_compress_device failed: %s" % ST_NAMES.get(rc, rc))
         return self.out, self.frame_off
 
 

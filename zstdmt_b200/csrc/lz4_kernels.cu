@@ -17,11 +17,14 @@
 //
 // The compressor's match/parse rule is deterministic and restated on the CPU in
 // oracle/lz4_oracle.c:orc_lz4_block_compress_b200 (tests compare bit-exact).
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include <vector>
 #include "common.cuh"
 #include "zmt_dev.h"
+#include "zstd_entropy.cuh"
 
 // bytes of chunk c: explicit per-chunk sizes (host pipeline: any fn_read may come back short)
 // or derived from a contiguous input of in_bytes cut every chunk_size bytes.
@@ -53,6 +56,7 @@ struct __align__(16) CompressSmem {
     uint8_t  pad0[16];                    // bytes "before" the block (read by the 8-byte window of phase 1, never matched)
     uint8_t  in[LZ4_BLK + 32];            // block bytes + zero pad
     uint32_t tab[1 << C_HASHLOG];         // hash -> 1 + position
+    // ---- tile arrays (dead between tiles: the zstd entropy stage aliases them, see ZEnt)
     uint16_t off[C_TILE];                 // per tile position: candidate offset (0 = none)
     uint8_t  len[C_TILE];                 // per piece start: piece length (<= 19)
     uint32_t M[C_TILE / 32];              // has-candidate bits
@@ -69,12 +73,15 @@ struct __align__(16) CompressSmem {
     uint16_t piece[C_MAXPIECE];           // tile-relative start of the r-th selected piece
     uint16_t hidx[C_MAXPIECE];            // piece index of the h-th head
     uint32_t longl[3 * (C_TILE / C_LONGLIT + 2)];
+    // ---- end of tile arrays
     uint32_t scanws[40];
     uint32_t nlong;
     uint32_t e_next;                      // chain state entering the next tile: position ...
     uint32_t d_next;                      // ... and offset of the match still open there (0 = free)
     uint64_t mbar;
 };
+
+static_assert(offsetof(CompressSmem, scanws) - offsetof(CompressSmem, off) >= sizeof(ZEnt), "entropy scratch must fit in the tile arrays");
 
 // number of bytes (<= cap) for which s[p + i] == s[p + i - d]
 __device__ __forceinline__ uint32_t c_extend(const uint8_t* s, uint32_t p, uint32_t d, uint32_t cap)
@@ -172,9 +179,12 @@ __device__ __forceinline__ uint32_t c_emit_seq(CompressSmem& S, uint8_t* dst, ui
     return (uint32_t)(op - (dst + o));
 }
 
+// CODEC 0: LZ4 block format out.  CODEC 1: Zstandard blocks out (same candidates + parse, entropy stage per ~16 KiB).
+template <int CODEC>
 __global__ void __launch_bounds__(C_NT, 2)
-lz4_compress_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32_t chunk_size, const uint32_t* __restrict__ chunk_bytes,
-                           uint32_t bpc, uint8_t* __restrict__ tmp, uint32_t* __restrict__ blk_csize, uint32_t nblocks, uint32_t flags)
+lz77_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32_t chunk_size, const uint32_t* __restrict__ chunk_bytes,
+                   uint32_t bpc, uint8_t* __restrict__ tmp, uint32_t* __restrict__ blk_csize, uint32_t nblocks, uint32_t flags,
+                   ZScratch* __restrict__ zscratch)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     CompressSmem& S = *reinterpret_cast<CompressSmem*>(smem_raw);
@@ -209,6 +219,12 @@ lz4_compress_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, ui
         uint32_t e = 0, e_din = 0, out_pos = 0;           // CTA-uniform parse state (position, offset of the open match)
         // pending sequence: its match may still grow in the next tile, so it is emitted one tile late
         uint32_t pd_valid = 0, pd_lit = 0, pd_start = 0, pd_off = 0, pd_end = 0;
+        // zstd: sequences / literals gathered for the current sub-block, content already emitted into blocks
+        ZScratch* const zs = CODEC == 1 ? zscratch + blockIdx.x : nullptr;
+        ZEnt& ZE = *reinterpret_cast<ZEnt*>(&S.off[0]);
+        uint32_t z_nseq = 0, z_nlit = 0, z_pos = 0, z_tiles = 0;
+        const bool z_last_of_chunk = (boff + n == cbytes);
+        auto cta_sync = [] () { CTA_SYNC(); };
 
         for (uint32_t t0 = 0; t0 < n; t0 += C_TILE) {
             // ---------------- phase 1: candidates (4 rounds of 1024 positions)
@@ -254,8 +270,9 @@ lz4_compress_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, ui
             const uint32_t t1 = t0 + C_TILE;
             __syncwarp();
             const int tile_has_match = __syncthreads_or(anyM != 0);
-            if ((!tile_has_match && !e_din) || e >= t1) { if (e < t1) e = t1; continue; }   // nothing to parse in this tile
-
+            const bool do_parse = !((!tile_has_match && !e_din) || e >= t1);
+            if (!do_parse) { if (e < t1) e = t1; }         // nothing to parse in this tile
+            else do {
             // ---------------- phase 2: speculative chains (own segment, then continuation)
             const uint32_t k0 = (e - t0) / C_SEG;
             const uint32_t seg0 = t0 + tid * C_SEG;
@@ -301,7 +318,7 @@ lz4_compress_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, ui
                 while (w) { const uint32_t b = __ffs(w) - 1; w &= w - 1; S.piece[base++] = (uint16_t)(tid * 32 + b); }
             }
             CTA_SYNC();
-            if (np == 0) continue;
+            if (np == 0) break;
             // piece r is a HEAD unless it continues the previous piece's match: flagged continuation, or contiguous with the
             // same offset (the effective offset of a flagged piece is that of the nearest unflagged piece before it)
             uint32_t nh_local = 0, headmask = 0;
@@ -335,7 +352,7 @@ lz4_compress_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, ui
             CTA_SYNC();
             const uint32_t lastp = S.piece[np - 1];
             const uint32_t tile_end = t0 + lastp + S.len[lastp];     // end of the last piece of this tile
-            if (nh == 0) { pd_end = tile_end; continue; }            // every piece extends the pending sequence
+            if (nh == 0) { pd_end = tile_end; break; }               // every piece extends the pending sequence
             if (pd_valid && S.hidx[0] > 0) { const uint32_t pb = S.piece[S.hidx[0] - 1]; pd_end = t0 + pb + S.len[pb]; }
             // sequences to emit now: [pending] + heads 0 .. nh-2 ; head nh-1 becomes the new pending sequence
             const uint32_t nemit = pd_valid + nh - 1;
@@ -355,24 +372,39 @@ lz4_compress_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, ui
                         else { const uint32_t pp = S.piece[pi - 1]; ls = t0 + pp + S.len[pp]; }
                     }
                     e_lit0[k] = ls; e_lit[k] = st - ls; e_off[k] = of; e_len[k] = en - st;
-                    sz += c_seq_size(e_lit[k], e_len[k]); cnt++;
+                    sz += CODEC == 0 ? c_seq_size(e_lit[k], e_len[k]) : ((1u << 18) | e_lit[k]); cnt++;   // zstd: (count, literal bytes) packed
                 }
             }
             uint32_t total;
-            uint32_t o = out_pos + block_exscan(sz, S.scanws, &total);
+            uint32_t o = block_exscan(sz, S.scanws, &total);
+            if (CODEC == 0) {
+                o += out_pos;
 #pragma unroll
-            for (uint32_t k = 0; k < 4; k++) {
-                if (k >= cnt) break;
-                o += c_emit_seq(S, dst, o, e_lit0[k], e_lit[k], e_off[k], e_len[k]);
+                for (uint32_t k = 0; k < 4; k++) {
+                    if (k >= cnt) break;
+                    o += c_emit_seq(S, dst, o, e_lit0[k], e_lit[k], e_off[k], e_len[k]);
+                }
+            } else {
+                uint32_t si = z_nseq + (o >> 18), li = z_nlit + (o & 0x3FFFF);
+#pragma unroll
+                for (uint32_t k = 0; k < 4; k++) {
+                    if (k >= cnt) break;
+                    ZSeq q; q.litlen = e_lit[k]; q.off = (uint16_t)e_off[k]; q.mlen = (uint16_t)e_len[k];
+                    zs->seq[si++] = q;
+                    if (e_lit[k] <= C_LONGLIT) { for (uint32_t i = 0; i < e_lit[k]; i++) zs->lit[li + i] = S.in[e_lit0[k] + i]; }
+                    else { const uint32_t s = atomicAdd(&S.nlong, 1u); S.longl[3 * s] = e_lit0[k]; S.longl[3 * s + 1] = li; S.longl[3 * s + 2] = e_lit[k]; }
+                    li += e_lit[k];
+                }
             }
             CTA_SYNC();
             {   // cooperative copies of long literal runs: one warp per run
                 const uint32_t nl = S.nlong;
+                uint8_t* const ldst = CODEC == 0 ? dst : zs->lit;
                 for (uint32_t s = wid; s < nl; s += C_NT / 32) {
                     const uint32_t sp = S.longl[3 * s], dp = S.longl[3 * s + 1], ln = S.longl[3 * s + 2];
-                    for (uint32_t i = lane; i < ln; i += 32) dst[dp + i] = S.in[sp + i];
+                    for (uint32_t i = lane; i < ln; i += 32) ldst[dp + i] = S.in[sp + i];
                 }
-                out_pos += total;
+                if (CODEC == 0) out_pos += total; else { z_nseq += total >> 18; z_nlit += total & 0x3FFFF; }
                 // new pending = last head of this tile
                 const uint32_t pi = S.hidx[nh - 1], pr = S.piece[pi];
                 uint32_t ls;
@@ -382,10 +414,44 @@ lz4_compress_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, ui
                 CTA_SYNC();
                 if (tid == 0) S.nlong = 0;
             }
+            } while (0);
+
+            if (CODEC == 1) {
+                // ---------------- zstd: close a block every 4 tiles (not at the end of the window: the final flush does that)
+                z_tiles++;
+                if ((z_tiles & 3) == 0 && t1 < n) {
+                    CTA_SYNC();
+                    // trailing literals up to C: everything before the pending match (or all parsed bytes when nothing is pending)
+                    const uint32_t cover = pd_valid ? pd_lit : z_pos;
+                    const uint32_t C = pd_valid ? pd_start : t1;
+                    for (uint32_t i = tid; i < C - cover; i += C_NT) zs->lit[z_nlit + i] = S.in[cover + i];
+                    const uint32_t nl = z_nlit + (C - cover);
+                    CTA_SYNC();
+                    if (C > z_pos) out_pos += z_encode_block(ZE, zs, z_nseq, nl, S.in + z_pos, C - z_pos, false, dst + out_pos, S.scanws, cta_sync);
+                    z_pos = C; if (pd_valid) pd_lit = C;
+                    z_nseq = 0; z_nlit = 0;
+                }
+            }
         }
 
         // ---------------- flush the pending sequence + last literals
-        {
+        if (CODEC == 1) {
+            CTA_SYNC();
+            uint32_t anchor = z_pos;
+            if (pd_valid) {
+                anchor = pd_end;
+                const uint32_t ll = pd_start - pd_lit;
+                if (tid == 0) { ZSeq q; q.litlen = ll; q.off = (uint16_t)pd_off; q.mlen = (uint16_t)(pd_end - pd_start); zs->seq[z_nseq] = q; }
+                for (uint32_t i = tid; i < ll; i += C_NT) zs->lit[z_nlit + i] = S.in[pd_lit + i];
+                z_nseq++; z_nlit += ll;
+            }
+            for (uint32_t i = tid; i < n - anchor; i += C_NT) zs->lit[z_nlit + i] = S.in[anchor + i];
+            z_nlit += n - anchor;
+            CTA_SYNC();
+            // the frame's last block carries the Last_Block bit; an empty raw block does when nothing is left
+            out_pos += z_encode_block(ZE, zs, z_nseq, z_nlit, S.in + z_pos, n - z_pos, z_last_of_chunk, dst + out_pos, S.scanws, cta_sync);
+            if (tid == 0) blk_csize[blk] = out_pos;
+        } else {
             uint32_t anchor = 0;
             if (pd_valid) {
                 anchor = pd_end;
@@ -784,6 +850,107 @@ __global__ void lz4_verify_kernel(const uint8_t* __restrict__ in, const uint64_t
     status[f] = st & 0xFF;
 }
 
+// ============================================================================ zstd frame pack
+// frame = 12 (skippable hdr) + magic 4 + FHD 1 + FCS (1 / 2 / 4) + the blocks of every 64 KiB window (+ an empty
+// last block for an empty chunk); no checksum, single segment — the layout ZSTD_compress gives the reference
+// (28 B5 2F FD A0 <LE32 size> for 1 MiB, 28 B5 2F FD 20 00 01 00 00 for empty input).
+__device__ __forceinline__ uint32_t zstd_fcs_bytes(uint64_t n) { return n <= 255 ? 1u : n <= 65791 ? 2u : 4u; }
+
+__global__ void zstd_frame_sizes_kernel(const uint32_t* __restrict__ blk_csize, uint64_t in_bytes, uint32_t chunk_size,
+                                        const uint32_t* __restrict__ chunk_bytes, uint32_t bpc, uint32_t nchunks, uint64_t* __restrict__ frame_size)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchunks) return;
+    const uint64_t cbytes = zmt_chunk_len(chunk_bytes, c, in_bytes, chunk_size);
+    uint64_t sz = 12 + 4 + 1 + zstd_fcs_bytes(cbytes);
+    if (cbytes == 0) sz += 3;
+    for (uint32_t b = 0; b < bpc; b++) sz += blk_csize[c * bpc + b];
+    frame_size[c] = sz;
+}
+
+__global__ void __launch_bounds__(256)
+zstd_frame_pack_kernel(uint64_t in_bytes, uint32_t chunk_size, const uint32_t* __restrict__ chunk_bytes, uint32_t bpc,
+                       const uint8_t* __restrict__ tmp, const uint32_t* __restrict__ blk_csize, const uint64_t* __restrict__ frame_off,
+                       uint8_t* __restrict__ out, uint32_t nblocks)
+{
+    for (uint32_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const uint32_t c = blk / bpc, b = blk % bpc;
+        const uint64_t cbytes = zmt_chunk_len(chunk_bytes, c, in_bytes, chunk_size);
+        const uint32_t fl = zstd_fcs_bytes(cbytes), hdr = 12 + 4 + 1 + fl;
+        uint8_t* f = out + frame_off[c];
+        const uint32_t cs = blk_csize[blk];
+        if (cs == 0 && b != 0) continue;
+        uint64_t pos = hdr;
+        for (uint32_t k = 0; k < b; k++) pos += blk_csize[c * bpc + k];
+        if (threadIdx.x == 0 && b == 0) {
+            const uint64_t fsz = frame_off[c + 1] - frame_off[c];
+            stg_le32(f, 0x184D2A50u); stg_le32(f + 4, 4); stg_le32(f + 8, (uint32_t)(fsz - 12));
+            stg_le32(f + 12, 0xFD2FB528u);
+            f[16] = fl == 1 ? 0x20 : fl == 2 ? 0x60 : 0xA0;
+            if (fl == 1) f[17] = (uint8_t)cbytes;
+            else if (fl == 2) { const uint32_t v = (uint32_t)cbytes - 256; f[17] = (uint8_t)v; f[18] = (uint8_t)(v >> 8); }
+            else stg_le32(f + 17, (uint32_t)cbytes);
+            if (cbytes == 0) { f[hdr] = 1; f[hdr + 1] = 0; f[hdr + 2] = 0; }        // empty raw last block
+        }
+        if (cs) coop_copy_g2g(f + pos, tmp + (uint64_t)blk * ZMT_LZ4_TMP_STRIDE, cs, threadIdx.x, blockDim.x);
+    }
+}
+
+// ---- predefined FSE encoding tables (RFC 8878 §3.1.1.3.2.2.1 distributions; FSE_buildCTable construction [ext])
+static void zstd_build_ctable(ZFseCTable& T, const int16_t* norm, int nsym, int log)
+{
+    const int size = 1 << log, step = (size >> 1) + (size >> 3) + 3;
+    int cumul[64], high = size - 1, pos = 0;
+    uint8_t sym[64];
+    memset(&T, 0, sizeof(T)); T.log = (uint32_t)log;
+    cumul[0] = 0;
+    for (int u = 1; u <= nsym; u++) {
+        if (norm[u - 1] == -1) { cumul[u] = cumul[u - 1] + 1; sym[high--] = (uint8_t)(u - 1); }
+        else cumul[u] = cumul[u - 1] + norm[u - 1];
+    }
+    for (int s = 0; s < nsym; s++)
+        for (int i = 0; i < norm[s]; i++) { sym[pos] = (uint8_t)s; do { pos = (pos + step) & (size - 1); } while (pos > high); }
+    for (int u = 0; u < size; u++) { const int s = sym[u]; T.state[cumul[s]++] = (uint16_t)(size + u); }
+    int total = 0;
+    for (int s = 0; s < nsym; s++) {
+        const int n = norm[s];
+        if (n == 0) { T.dnb[s] = ((log + 1) << 16) - (1 << log); T.dfs[s] = 0; }
+        else if (n == -1 || n == 1) { T.dnb[s] = (log << 16) - (1 << log); T.dfs[s] = total - 1; total++; }
+        else {
+            int hb = 0; while ((1 << (hb + 1)) <= n - 1) hb++;
+            const int maxBitsOut = log - hb, minStatePlus = n << maxBitsOut;
+            T.dnb[s] = (maxBitsOut << 16) - minStatePlus; T.dfs[s] = total - n; total += n;
+        }
+    }
+}
+
+static int zstd_tables_init()
+{
+    static std::vector<int> done;                 // devices whose __constant__ copies are loaded
+    int dev = 0; if (cudaGetDevice(&dev) != cudaSuccess) return ZMT_ST_CUDA;
+    for (int d : done) if (d == dev) return ZMT_ST_OK;
+    static const int16_t LLn[36] = { 4,3,2,2,2,2,2,2,2,2,2,2,2,1,1,1,2,2,2,2,2,2,2,2,2,3,2,1,1,1,1,1,-1,-1,-1,-1 };
+    static const int16_t MLn[53] = { 1,4,3,2,2,2,2,2,2,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,-1,-1,-1,-1,-1,-1,-1 };
+    static const int16_t OFn[29] = { 1,1,1,1,1,1,2,2,2,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,-1,-1,-1,-1,-1 };
+    static const uint32_t LLb[36] = { 0,1,2,3,4,5,6,7,8,9,10,11,12,13,14,15,16,18,20,22,24,28,32,40,48,64,128,256,512,1024,2048,4096,8192,16384,32768,65536 };
+    static const uint8_t  LLx[36] = { 0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,1,1,1,1,2,2,3,3,4,6,7,8,9,10,11,12,13,14,15,16 };
+    static const uint32_t MLb[53] = { 3,4,5,6,7,8,9,10,11,12,13,14,15,16,17,18,19,20,21,22,23,24,25,26,27,28,29,30,31,32,33,34,35,37,39,41,43,47,51,59,67,83,99,131,259,515,1027,2051,4099,8195,16387,32771,65539 };
+    static const uint8_t  MLx[53] = { 0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,1,1,1,1,2,2,3,3,4,4,5,7,8,9,10,11,12,13,14,15,16 };
+    ZFseCTable t;
+    zstd_build_ctable(t, LLn, 36, 6); if (cudaMemcpyToSymbol(c_fse_ll, &t, sizeof(t)) != cudaSuccess) return ZMT_ST_CUDA;
+    zstd_build_ctable(t, OFn, 29, 5); if (cudaMemcpyToSymbol(c_fse_of, &t, sizeof(t)) != cudaSuccess) return ZMT_ST_CUDA;
+    zstd_build_ctable(t, MLn, 53, 6); if (cudaMemcpyToSymbol(c_fse_ml, &t, sizeof(t)) != cudaSuccess) return ZMT_ST_CUDA;
+    uint8_t llc[64], mlc[128];
+    for (int v = 0; v < 64; v++) { int c = 0; while (c + 1 < 36 && LLb[c + 1] <= (uint32_t)v) c++; llc[v] = (uint8_t)c; }
+    for (int v = 0; v < 128; v++) { int c = 0; while (c + 1 < 53 && MLb[c + 1] <= (uint32_t)v + 3) c++; mlc[v] = (uint8_t)c; }
+    cudaMemcpyToSymbol(c_ll_code, llc, sizeof(llc)); cudaMemcpyToSymbol(c_ml_code, mlc, sizeof(mlc));
+    cudaMemcpyToSymbol(c_ll_base, LLb, sizeof(LLb)); cudaMemcpyToSymbol(c_ml_base, MLb, sizeof(MLb));
+    cudaMemcpyToSymbol(c_ll_bits, LLx, sizeof(LLx)); cudaMemcpyToSymbol(c_ml_bits, MLx, sizeof(MLx));
+    if (cudaGetLastError() != cudaSuccess) return ZMT_ST_CUDA;
+    done.push_back(dev);
+    return ZMT_ST_OK;
+}
+
 // ============================================================================ host launchers
 // ZSTDMT_B200_DEBUG_SYNC=1: synchronise after every kernel and name the one that failed (debug only)
 // ---- optional per-kernel timing (zmt_prof_begin / zmt_prof_end): CUDA events recorded on the launching
@@ -871,11 +1038,11 @@ extern "C" int zmt_lz4_compress_device(const void* d_in, uint64_t in_bytes, uint
     uint32_t* chk = (uint32_t*)w; w += (((uint64_t)nchunks * 4 + 255) & ~255ull);
     uint64_t* frame_size = (uint64_t*)w;
 
-    cudaFuncSetAttribute(lz4_compress_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CompressSmem));
+    cudaFuncSetAttribute(lz77_blocks_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CompressSmem));
     const uint32_t maxc = (uint32_t)(zmt_sm_count() * 2 * 8);
     uint32_t gridc = nblocks < maxc ? nblocks : maxc;
     { ZmtProfScope ps(ZMT_K_LZ4_COMPRESS, stream);
-    lz4_compress_blocks_kernel<<<gridc, C_NT, sizeof(CompressSmem), stream>>>((const uint8_t*)d_in, in_bytes, chunk_size, d_chunk_bytes, bpc, tmp, blk_csize, nblocks, getenv("ZSTDMT_B200_NO_TMA") ? 1u : 0u); }
+    lz77_blocks_kernel<0><<<gridc, C_NT, sizeof(CompressSmem), stream>>>((const uint8_t*)d_in, in_bytes, chunk_size, d_chunk_bytes, bpc, tmp, blk_csize, nblocks, getenv("ZSTDMT_B200_NO_TMA") ? 1u : 0u, nullptr); }
     zmt_dbg_check(stream, "lz4_compress_blocks_kernel");
     { ZmtProfScope ps(ZMT_K_XXH32, stream);
     xxh32_kernel<<<(nchunks + X_WARPS - 1) / X_WARPS, 32 * X_WARPS, 0, stream>>>((const uint8_t*)d_in, nullptr, nullptr, d_chunk_bytes, chunk_size, in_bytes, chk, nchunks); }
@@ -891,6 +1058,59 @@ extern "C" int zmt_lz4_compress_device(const void* d_in, uint64_t in_bytes, uint
     { ZmtProfScope ps(ZMT_K_LZ4_PACK, stream);
     lz4_frame_pack_kernel<<<gridp, 256, 0, stream>>>((const uint8_t*)d_in, in_bytes, chunk_size, d_chunk_bytes, bpc, tmp, blk_csize, chk, d_frame_off, (uint8_t*)d_out, nblocks); }
     zmt_dbg_check(stream, "lz4_frame_pack_kernel");
+    return cudaGetLastError() == cudaSuccess ? ZMT_ST_OK : ZMT_ST_CUDA;
+}
+
+// ---------------------------------------------------------------- zstd compress
+static inline uint32_t zstd_grid(uint32_t nblocks) { const uint32_t m = (uint32_t)(zmt_sm_count() * 2 * 4); return nblocks < m ? nblocks : m; }
+
+extern "C" size_t zmt_zstdc_workspace_bytes(uint32_t nchunks, uint32_t chunk_size)
+{
+    if (chunk_size == 0) return 0;
+    const uint64_t bpc = ((uint64_t)chunk_size + LZ4_BLK - 1) / LZ4_BLK;
+    const uint64_t nblocks = (uint64_t)nchunks * bpc;
+    uint64_t sz = nblocks * ZMT_LZ4_TMP_STRIDE;
+    sz += ((nblocks * 4 + 255) & ~255ull);
+    sz += ((((uint64_t)nchunks + 1) * 8 + 255) & ~255ull);
+    sz += (uint64_t)(148 * 2 * 4 + 8) * ((sizeof(ZScratch) + 255) & ~255ull);      // per-CTA scratch, sized for the largest grid we launch
+    return (size_t)sz + 1024;
+}
+
+extern "C" uint64_t zmt_zstdc_out_bound(uint32_t nchunks, uint32_t chunk_size)
+{
+    if (chunk_size == 0) return 0;
+    const uint64_t bpc = ((uint64_t)chunk_size + LZ4_BLK - 1) / LZ4_BLK;
+    return (uint64_t)nchunks * ((uint64_t)chunk_size + 12 + 9 + 3 + 32 * bpc) + 256;     // <= 5 blocks x 3-byte headers per 64 KiB window
+}
+
+extern "C" int zmt_zstd_compress_device(const void* d_in, uint64_t in_bytes, uint32_t chunk_size, const uint32_t* d_chunk_bytes,
+                                        uint32_t nchunks, void* d_work, void* d_out, uint64_t* d_frame_off, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (chunk_size == 0 || nchunks == 0) return ZMT_ST_BAD_ARG;
+    if (!d_chunk_bytes && nchunks != zmt_chunk_count(in_bytes, chunk_size)) return ZMT_ST_BAD_ARG;
+    const uint32_t bpc = (uint32_t)(((uint64_t)chunk_size + LZ4_BLK - 1) / LZ4_BLK);
+    if ((uint64_t)nchunks * bpc > 0x7FFFFFFFull) return ZMT_ST_BAD_ARG;
+    const int ti = zstd_tables_init(); if (ti != ZMT_ST_OK) return ti;
+    const uint32_t nblocks = nchunks * bpc;
+    uint8_t* w = (uint8_t*)d_work;
+    uint8_t* tmp = w; w += (uint64_t)nblocks * ZMT_LZ4_TMP_STRIDE;
+    uint32_t* blk_csize = (uint32_t*)w; w += (((uint64_t)nblocks * 4 + 255) & ~255ull);
+    uint64_t* frame_size = (uint64_t*)w; w += ((((uint64_t)nchunks + 1) * 8 + 255) & ~255ull);
+    ZScratch* zsc = (ZScratch*)w;
+    static_assert(sizeof(ZScratch) % 8 == 0, "scratch stride");
+    cudaFuncSetAttribute(lz77_blocks_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CompressSmem));
+    const uint32_t gridc = zstd_grid(nblocks);
+    { ZmtProfScope ps(ZMT_K_ZSTD_COMPRESS, stream);
+    lz77_blocks_kernel<1><<<gridc, C_NT, sizeof(CompressSmem), stream>>>((const uint8_t*)d_in, in_bytes, chunk_size, d_chunk_bytes, bpc, tmp, blk_csize, nblocks, getenv("ZSTDMT_B200_NO_TMA") ? 1u : 0u, zsc); }
+    zmt_dbg_check(stream, "lz77_blocks_kernel<zstd>");
+    zstd_frame_sizes_kernel<<<(nchunks + 255) / 256, 256, 0, stream>>>(blk_csize, in_bytes, chunk_size, d_chunk_bytes, bpc, nchunks, frame_size);
+    scan_u64_kernel<<<1, 1024, 0, stream>>>(frame_size, d_frame_off, nchunks);
+    const uint32_t maxp = (uint32_t)(zmt_sm_count() * 16);
+    const uint32_t gridp = nblocks < maxp ? nblocks : maxp;
+    { ZmtProfScope ps(ZMT_K_ZSTD_PACK, stream);
+    zstd_frame_pack_kernel<<<gridp, 256, 0, stream>>>(in_bytes, chunk_size, d_chunk_bytes, bpc, tmp, blk_csize, d_frame_off, (uint8_t*)d_out, nblocks); }
+    zmt_dbg_check(stream, "zstd_frame_pack_kernel");
     return cudaGetLastError() == cudaSuccess ? ZMT_ST_OK : ZMT_ST_CUDA;
 }
 
