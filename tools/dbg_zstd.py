@@ -20,6 +20,16 @@ if o.have_ref():
     for T in (1, 3):
         rc, b2, st = o.ref_decompress(o.CODEC_ZSTD, f, n, threads=T)
         print("libzstd (reference T=%d) rc %d ok %s" % (T, rc, b2.size == n and np.array_equal(b2, src)))
+dec = z.ZstdDeviceDecompressor(f)
+print("scan", set(dec.scan_status), "frames", dec.n, "blocks", dec.nblk)
+d_f = torch.from_numpy(f).cuda()
+dout, st = dec.run(d_f); torch.cuda.synchronize()
+print("GPU decode status", st.cpu().unique().tolist(), "ok", dec.out_total == n and np.array_equal(dout[:n].cpu().numpy(), src))
+# callback API both ways
+rc, fr2, stt = z.compress_mem(z.CODEC_ZSTD, src, threads=4, level=3, chunk=chunk)
+print("ZSTDCB_compressCCtx rc", rc, "same bytes as device path", fr2.size == f.size and np.array_equal(fr2, f), stt)
+rc, bk, stt = z.decompress_mem(z.CODEC_ZSTD, fr2, n + 16, threads=4)
+print("ZSTDCB_decompressDCtx rc", rc, "ok", bk.size == n and np.array_equal(bk, src), stt)
 if os.environ.get("TIME"):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(2): comp.run(d_in)
@@ -27,4 +37,10 @@ if os.environ.get("TIME"):
     for _ in range(5): comp.run(d_in)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
-    print("ms/step %.3f  in GB/s %.1f" % (ms, n / ms / 1e6))
+    print("compress ms/step %.3f  in GB/s %.1f" % (ms, n / ms / 1e6))
+    for _ in range(2): dec.run(d_f)
+    e0.record()
+    for _ in range(5): dec.run(d_f)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    print("decompress ms/step %.3f  out GB/s %.1f" % (ms, n / ms / 1e6))

@@ -29,11 +29,15 @@
 #include "zmt_dev.h"
 
 extern "C" {
-size_t   zmt_zstdc_workspace_bytes(uint32_t nchunks, uint32_t chunk_size) __attribute__((weak));
-uint64_t zmt_zstdc_out_bound(uint32_t nchunks, uint32_t chunk_size) __attribute__((weak));
-int      zmt_zstd_compress_device(const void*, uint64_t, uint32_t, const uint32_t*, uint32_t, void*, void*, uint64_t*, void*) __attribute__((weak));
-size_t   zmt_zstdd_workspace_bytes(uint32_t nframes) __attribute__((weak));
-int      zmt_zstd_decompress_device(const void*, uint64_t, const uint64_t*, const uint32_t*, uint32_t, uint32_t, void*, const uint64_t*, uint64_t*, uint32_t*, void*, void*) __attribute__((weak));
+size_t   zmt_zstdc_workspace_bytes(uint32_t nchunks, uint32_t chunk_size);
+uint64_t zmt_zstdc_out_bound(uint32_t nchunks, uint32_t chunk_size);
+int      zmt_zstd_compress_device(const void*, uint64_t, uint32_t, const uint32_t*, uint32_t, void*, void*, uint64_t*, void*);
+size_t   zmt_zstd_blk_desc_bytes(void);
+int      zmt_zstd_scan_frame_host(const uint8_t* frame, size_t n, uint64_t base_off, uint32_t frame_idx, void* blocks_out, uint32_t* nblocks_io,
+                                  uint32_t max_blocks, uint64_t* scratch_used, uint64_t* content_size);
+size_t   zmt_zstdd_workspace_bytes(uint32_t nframes, uint32_t nblocks, uint64_t scratch_bytes);
+int      zmt_zstd_decompress_device(const void* d_in, const void* d_blocks, uint32_t nblocks, const uint32_t* d_frame_first_blk, const uint64_t* d_expect,
+                                    uint32_t nframes, void* d_out, const uint64_t* d_out_off, uint64_t* d_out_size, uint32_t* d_status, void* d_work, void* stream);
 }
 
 namespace {
@@ -107,15 +111,13 @@ struct CodecOps {
     size_t   (*c_work)(uint32_t nchunks, uint32_t chunk);
     uint64_t (*c_bound)(uint32_t nchunks, uint32_t chunk);
     int      (*compress)(const void*, uint64_t, uint32_t, const uint32_t*, uint32_t, void*, void*, uint64_t*, void*);
-    size_t   (*d_work)(uint32_t nframes);
-    int      (*decompress)(const void*, uint64_t, const uint64_t*, const uint32_t*, uint32_t, uint32_t, void*, const uint64_t*, uint64_t*, uint32_t*, void*, void*);
 };
 
 
 const CodecOps* codec_ops(int codec)
 {
-    static const CodecOps lz4 = { zmt_lz4c_workspace_bytes, zmt_lz4c_out_bound, zmt_lz4_compress_device, zmt_lz4d_workspace_bytes, zmt_lz4_decompress_device };
-    static const CodecOps zstd = { zmt_zstdc_workspace_bytes, zmt_zstdc_out_bound, zmt_zstd_compress_device, zmt_zstdd_workspace_bytes, zmt_zstd_decompress_device };
+    static const CodecOps lz4 = { zmt_lz4c_workspace_bytes, zmt_lz4c_out_bound, zmt_lz4_compress_device };
+    static const CodecOps zstd = { zmt_zstdc_workspace_bytes, zmt_zstdc_out_bound, zmt_zstd_compress_device };
     return codec == CODEC_LZ4 ? &lz4 : &zstd;
 }
 
@@ -131,17 +133,20 @@ struct Slot {
     // batch contents
     uint32_t n = 0;              // chunks / frames in this batch
     uint32_t max_bpf = 1;        // decompress: max 64 KiB blocks per frame in this batch
+    // zstd decompress: block descriptors built by the reader (pinned) + device copy, scratch demand of the batch
+    uint8_t *h_blk = nullptr, *d_blk = nullptr; uint32_t blk_cap = 0, nblk = 0; uint64_t scratch_used = 0;
     size_t in_used = 0, out_used = 0;
     int state = 0;               // 0 free, 1 filled, 2 submitted
     bool ok = false;
 };
 
-// table layout (entries = tab_cap):  u64 a[cap+1] | u64 b[cap+1] | u64 c[cap+1] | u32 d[cap] | u32 e[cap]
-struct Tables { uint64_t *a, *b, *c; uint32_t *d, *e; };
-inline size_t tables_bytes(size_t cap) { return 3 * (cap + 1) * 8 + 2 * cap * 4 + 64; }
+// table layout (entries = tab_cap):  u64 a[cap+1] | u64 b[cap+1] | u64 c[cap+1] | u64 f[cap+1] | u32 d[cap] | u32 e[cap] | u32 g[cap+1]
+struct Tables { uint64_t *a, *b, *c, *f; uint32_t *d, *e, *g; };
+inline size_t tables_bytes(size_t cap) { return 4 * (cap + 1) * 8 + 2 * cap * 4 + (cap + 1) * 4 + 64; }
 inline Tables tables_at(uint8_t* base, size_t cap)
 {
-    Tables t; t.a = (uint64_t*)base; t.b = t.a + cap + 1; t.c = t.b + cap + 1; t.d = (uint32_t*)(t.c + cap + 1); t.e = t.d + cap; return t;
+    Tables t; t.a = (uint64_t*)base; t.b = t.a + cap + 1; t.c = t.b + cap + 1; t.f = t.c + cap + 1;
+    t.d = (uint32_t*)(t.f + cap + 1); t.e = t.d + cap; t.g = t.e + cap; return t;
 }
 
 void slot_free_raw(Slot& s)
@@ -155,6 +160,8 @@ void slot_free_raw(Slot& s)
     if (s.d_out) cudaFree(s.d_out);
     if (s.d_work) cudaFree(s.d_work);
     if (s.d_tab) cudaFree(s.d_tab);
+    if (s.h_blk) cudaFreeHost(s.h_blk);
+    if (s.d_blk) cudaFree(s.d_blk);
     if (s.ev) cudaEventDestroy(s.ev);
     if (s.stream) cudaStreamDestroy(s.stream);
     s = Slot();
@@ -212,6 +219,20 @@ void slot_free(Slot& s)
         if (g_pool.size() < kPoolMax && !getenv("ZSTDMT_B200_NO_POOL")) { g_pool.push_back(s); s = Slot(); return; }
     }
     slot_free_raw(s);
+}
+
+bool slot_ensure_blocks(Slot& s, uint32_t cap)
+{
+    if (s.blk_cap >= cap) return true;
+    cudaSetDevice(s.dev);
+    if (s.h_blk) cudaFreeHost(s.h_blk);
+    if (s.d_blk) cudaFree(s.d_blk);
+    s.h_blk = s.d_blk = nullptr; s.blk_cap = 0;
+    const size_t bytes = (size_t)cap * zmt_zstd_blk_desc_bytes();
+    if (cudaHostAlloc((void**)&s.h_blk, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (cudaMalloc((void**)&s.d_blk, bytes) != cudaSuccess) { cudaGetLastError(); return false; }
+    s.blk_cap = cap;
+    return true;
 }
 
 // ------------------------------------------------------------------ pipeline state shared by the 3 threads
@@ -429,9 +450,9 @@ size_t read_some(const ErrCodes& E, GenRdWr* rw, void* dst, size_t want, size_t*
 size_t decompress_run(Ctx* c, GenRdWr* rw)
 {
     const ErrCodes& E = *c->E;
-    const CodecOps* ops = codec_ops(c->codec);
-    if (!ops->decompress || !ops->d_work) { c->lib_errcode = ZMT_ST_UNSUPPORTED; return E.library; }
     Pipe& P = c->pipe;
+    const bool is_zstd = c->codec == CODEC_ZSTD;
+    const uint32_t kBlkCap = 32768;
     // decode batches must hold enough frames to fill the GPU (one warp per 64 KiB block): 32 MiB of frames measured best
     const size_t in_cap0 = (env_size("ZSTDMT_B200_DBATCH_MB", 32) << 20), out_cap0 = in_cap0 * 2, tab_cap = 8192;
 
@@ -477,7 +498,11 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
         int per_dev = c->threads >= 4 ? 4 : c->threads >= 3 ? 3 : 2;
         P.slots.resize(c->devs.size() * per_dev);
         for (size_t i = 0; i < P.slots.size(); i++)
-            if (!slot_alloc(P.slots[i], c->devs[i % c->devs.size()], in_cap0, out_cap0, ops->d_work((uint32_t)tab_cap), tab_cap)) { ctx_release_slots(c); return E.mem; }
+        {
+            // zstd scratch: 16 B per sequence + the literals: ~2x the output on text, bounded at 3x + tables (the reader closes a batch early otherwise)
+            const size_t wk = is_zstd ? zmt_zstdd_workspace_bytes((uint32_t)tab_cap, kBlkCap, 3 * (uint64_t)out_cap0) : zmt_lz4d_workspace_bytes((uint32_t)tab_cap);
+            if (!slot_alloc(P.slots[i], c->devs[i % c->devs.size()], in_cap0, out_cap0, wk, tab_cap) || (is_zstd && !slot_ensure_blocks(P.slots[i], kBlkCap))) { ctx_release_slots(c); return E.mem; }
+        }
     }
     const size_t N = P.slots.size();
     P.fill_seq = P.submit_seq = P.write_seq = 0; P.reader_done = false; P.error = 0;
@@ -499,18 +524,27 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
             Tables T = tables_at(s->h_tab, s->tab_cap);
             uint32_t n = 0; size_t in_used = 0; uint64_t out_used = 0; size_t stat_in = 0;
             bool failed = false;
+            uint32_t nblk = 0; uint64_t scr = 0;                 // zstd: block descriptors + scratch demand of this batch
+            const uint64_t scr_cap = is_zstd ? 3 * (uint64_t)s->out_cap : 0;
             auto grow = [&](size_t need_in, uint64_t need_out) -> bool {   // empty slot too small for one frame: reallocate it
                 if (need_in <= s->in_cap && need_out <= s->out_cap) return true;
                 const int dev = s->dev; const size_t nin = need_in > s->in_cap ? need_in : s->in_cap, nout = need_out > s->out_cap ? (size_t)need_out : s->out_cap;
-                const size_t wk = s->work_cap, tc = s->tab_cap;
+                const size_t tc = s->tab_cap;
+                const size_t wk = is_zstd ? zmt_zstdd_workspace_bytes((uint32_t)tc, kBlkCap, 3 * (uint64_t)nout) : s->work_cap;
                 slot_free(*s);
-                return slot_alloc(*s, dev, nin, nout, wk, tc);
+                return slot_alloc(*s, dev, nin, nout, wk, tc) && (!is_zstd || slot_ensure_blocks(*s, kBlkCap));
             };
             if (!carry.empty()) {
                 if (!grow(carry.size(), carry_out)) { P.fail(E.mem); break; }
                 T = tables_at(s->h_tab, s->tab_cap);
                 memcpy(s->h_in, carry.data(), carry.size());
                 T.a[0] = 0; T.d[0] = (uint32_t)(carry.size() - 12); T.b[0] = 0;
+                if (is_zstd) {
+                    uint64_t cs = 0; T.g[0] = 0;
+                    int zr = zmt_zstd_scan_frame_host(s->h_in + 12, carry.size() - 12, 12, 0, s->h_blk, &nblk, s->blk_cap, &scr, &cs);
+                    if (zr != ZMT_ST_OK) { c->lib_errcode = (size_t)zr; P.fail(E.library); break; }
+                    T.f[0] = cs;
+                }
                 in_used = carry.size(); out_used = carry_out; n = 1; carry.clear();
             }
             while (n < s->tab_cap) {
@@ -542,6 +576,17 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
                 uint64_t osz = 0; bool okh = c->codec == CODEC_LZ4 ? lz4f_out_size(dstp + 12, toRead, c->frames + n, &osz) : zstd_out_size(dstp + 12, toRead, &osz);
                 if (!okh) { c->lib_errcode = ZMT_ST_BAD_HEADER; P.fail(c->codec == CODEC_LZ4 ? E.library : E.library); failed = true; break; }
                 if (to_carry) { carry_out = osz; break; }
+                uint32_t nblk_new = nblk; uint64_t scr_new = scr;
+                if (is_zstd) {
+                    // block table of this frame (descriptors are appended; rolled back if the frame moves to the next batch)
+                    uint64_t cs = 0;
+                    int zr = zmt_zstd_scan_frame_host(dstp + 12, toRead, in_used + 12, n, s->h_blk, &nblk_new, s->blk_cap, &scr_new, &cs);
+                    if (zr == ZMT_ST_DST_SMALL && n > 0) { carry.assign(dstp, dstp + 12 + toRead); carry_out = osz; break; }
+                    if (zr != ZMT_ST_OK) { c->lib_errcode = (size_t)zr; P.fail(zr == ZMT_ST_TRUNCATED || zr == ZMT_ST_TRAILING ? E.frame_decompress : E.library); failed = true; break; }
+                    if (scr_new > scr_cap && n > 0) { carry.assign(dstp, dstp + 12 + toRead); carry_out = osz; break; }
+                    if (scr_new > scr_cap) { c->lib_errcode = ZMT_ST_DST_SMALL; P.fail(E.library); failed = true; break; }
+                    osz = cs;
+                }
                 if (out_used + osz > s->out_cap) {
                     if (n == 0) {
                         // single frame larger than the slot: grow (payload already sits in h_in -> save it first)
@@ -549,14 +594,21 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
                         if (!grow(12 + toRead, osz)) { P.fail(E.mem); failed = true; break; }
                         T = tables_at(s->h_tab, s->tab_cap);
                         memcpy(s->h_in, save.data(), save.size());
+                        if (is_zstd) {                     // the block table lived in the old slot: rebuild it
+                            uint64_t cs = 0; nblk_new = 0; scr_new = 0;
+                            int zr = zmt_zstd_scan_frame_host(s->h_in + 12, toRead, 12, 0, s->h_blk, &nblk_new, s->blk_cap, &scr_new, &cs);
+                            if (zr != ZMT_ST_OK) { c->lib_errcode = (size_t)zr; P.fail(E.library); failed = true; break; }
+                        }
                     } else { carry.assign(dstp, dstp + 12 + toRead); carry_out = osz; break; }
                 }
                 T.a[n] = in_used; T.d[n] = (uint32_t)toRead; T.b[n] = out_used;
+                if (is_zstd) { T.g[n] = nblk; T.f[n] = osz; nblk = nblk_new; scr = scr_new; }
                 in_used += 12 + toRead; out_used += osz; n++;
             }
             if (failed) break;
             if (n == 0) break;
             T.b[n] = out_used;
+            if (is_zstd) { T.g[n] = nblk; s->nblk = nblk; s->scratch_used = scr; }
             s->n = n; s->in_used = in_used; s->out_used = (size_t)out_used;
             { uint64_t mx = 1; for (uint32_t i = 0; i < n; i++) { const uint64_t o = T.b[i + 1] - T.b[i]; const uint64_t nb = (o + 65535) / 65536; if (nb > mx) mx = nb; } s->max_bpf = (uint32_t)mx; }
             {
@@ -616,7 +668,9 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
         cudaError_t ce = cudaMemcpyAsync(s->d_in, s->h_in, s->in_used, cudaMemcpyHostToDevice, s->stream);
         if (ce == cudaSuccess) ce = cudaMemcpyAsync(s->d_tab, s->h_tab, s->tab_bytes, cudaMemcpyHostToDevice, s->stream);
         int st = ZMT_ST_CUDA;
-        if (ce == cudaSuccess) st = ops->decompress(s->d_in, s->in_used, Td.a, Td.d, s->n, s->max_bpf, s->d_out, Td.b, Td.c, Td.e, s->d_work, s->stream);
+        if (ce == cudaSuccess && is_zstd && s->nblk) ce = cudaMemcpyAsync(s->d_blk, s->h_blk, (size_t)s->nblk * zmt_zstd_blk_desc_bytes(), cudaMemcpyHostToDevice, s->stream);
+        if (ce == cudaSuccess) st = is_zstd ? zmt_zstd_decompress_device(s->d_in, s->d_blk, s->nblk, Td.g, Td.f, s->n, s->d_out, Td.b, Td.c, Td.e, s->d_work, s->stream)
+                                            : zmt_lz4_decompress_device(s->d_in, s->in_used, Td.a, Td.d, s->n, s->max_bpf, s->d_out, Td.b, Td.c, Td.e, s->d_work, s->stream);
         if (st == ZMT_ST_OK) {
             if (s->out_used) ce = cudaMemcpyAsync(s->h_out, s->d_out, s->out_used, cudaMemcpyDeviceToHost, s->stream);
             if (ce == cudaSuccess) ce = cudaMemcpyAsync(Th.c, Td.c, (size_t)s->n * 8, cudaMemcpyDeviceToHost, s->stream);
