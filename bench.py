@@ -287,6 +287,73 @@ def run_b200(args):
         assert np.array_equal(back[: 1 << 22], src[: 1 << 22]) and np.array_equal(back[n - (1 << 20): n], src[n - (1 << 20):])
         del back
 
+    if not args.no_extra:
+        # ---- BASELINE config 4 class: zstd-mt level 3 on synthetic text, 1 MiB chunks (2 GiB sample), device-timed + e2e
+        del comp
+        torch.cuda.empty_cache()
+        zn = min(n, 2 << 30)
+        ztxt = z.gen_stream(z.GEN_TEXT, zn, chunk, first=rank, stride=world)
+        zd_in = d_in[:zn]; zd_in.copy_(torch.from_numpy(ztxt))
+        zc = z.ZstdDeviceCompressor(zn, chunk)
+        for _ in range(3):
+            zc.run(zd_in, stream)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            zc.run(zd_in, stream)
+        e1.record(stream); torch.cuda.synchronize()
+        zms = e0.elapsed_time(e1) / args.steps
+        zframed = int(zc.frame_off[-1].item())
+        zf_host = zc.out[:zframed].cpu().numpy()
+        zdec = z.ZstdDeviceDecompressor(zf_host)
+        zout, zst = zdec.run(zc.out, stream); torch.cuda.synchronize()
+        assert int(zst.abs().sum().item()) == 0 and torch.equal(zout[:zn], zd_in), "zstd round trip mismatch"
+        for _ in range(2):
+            zdec.run(zc.out, stream)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(args.steps):
+            zdec.run(zc.out, stream)
+        e1.record(stream); torch.cuda.synchronize()
+        zdms = e0.elapsed_time(e1) / args.steps
+        zh = np.empty(z.mt_bound(zn, chunk), np.uint8)
+        L.zmt_zstd_compress_mem(threads, 3, chunk, ztxt.ctypes.data, zn, zh.ctypes.data, zh.size, st)
+        t = time.perf_counter()
+        rc = L.zmt_zstd_compress_mem(threads, 3, chunk, ztxt.ctypes.data, zn, zh.ctypes.data, zh.size, st)
+        ze = time.perf_counter() - t
+        assert rc == 0 and int(st[0]) == zframed
+        zb = np.empty(zn + 16, np.uint8)
+        L.zmt_zstd_decompress_mem(threads, 0, zh.ctypes.data, zframed, zb.ctypes.data, zn + 16, st)
+        t = time.perf_counter()
+        rc = L.zmt_zstd_decompress_mem(threads, 0, zh.ctypes.data, zframed, zb.ctypes.data, zn + 16, st)
+        zde = time.perf_counter() - t
+        assert rc == 0 and np.array_equal(zb[: 1 << 22], ztxt[: 1 << 22])
+        extra["zstd"] = {"workload": "zstd-mt level 3 (predefined FSE tables), %d MiB synthetic text, 1 MiB chunks (BASELINE configs[3] class)" % (zn >> 20),
+                         "ratio": zn / zframed, "compress_device_gbs": (zn + zframed) / (zms * 1e-3) / 1e9, "compress_ms": zms,
+                         "decompress_device_gbs": (zn + zframed) / (zdms * 1e-3) / 1e9, "decompress_ms": zdms,
+                         "compress_e2e_gbs": (zn + zframed) / ze / 1e9, "decompress_e2e_gbs": (zn + zframed) / zde / 1e9}
+        if world == 1:
+            try:
+                import _oracle as o
+                if o.have_ref():
+                    T = min(os.cpu_count() or 1, 128)
+                    capr = zn + zn // 64 + (1 << 20); outr = np.empty(capr, np.uint8); s5 = (ctypes.c_size_t * 5)()
+                    best = None
+                    for _ in range(2):
+                        tt = time.perf_counter(); rc = o.ref().ref_zstd_compress_mem(T, 3, chunk, ztxt.ctypes.data, zn, outr.ctypes.data, capr, s5); dt = time.perf_counter() - tt
+                        assert rc == 0; best = dt if best is None else min(best, dt)
+                    rfr = int(s5[0])
+                    extra["zstd"]["reference_cpu"] = {"threads": T, "compress_gbs": (zn + rfr) / best / 1e9, "ratio": zn / rfr}
+                    bestd = None
+                    for _ in range(2):
+                        tt = time.perf_counter(); rc = o.ref().ref_zstd_decompress_mem(T, 0, outr.ctypes.data, rfr, zb.ctypes.data, zn + 16, s5); dt = time.perf_counter() - tt
+                        assert rc == 0; bestd = dt if bestd is None else min(bestd, dt)
+                    extra["zstd"]["reference_cpu"]["decompress_gbs"] = (zn + rfr) / bestd / 1e9
+            except Exception as e:
+                extra["zstd"]["reference_cpu"] = {"error": repr(e)}
+        del zc, zdec, zout, zh, zb
+
     line = {
         "metric": "lz4-mt level-1 compress throughput, bytes in + framed bytes out", "value": value, "unit": "GB/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,

@@ -232,7 +232,7 @@ class ZstdDeviceDecompressor:
         offs, sizes = scan_frames(fb)
         self.n = len(offs)
         dsz = L.zmt_zstd_blk_desc_bytes()
-        cap = max(64, int(fb.size // 16 + 8 * self.n + 64))
+        cap = int(fb.size // 3 + self.n + 16)              # every block costs at least its 3-byte header
         blocks = np.zeros(cap * dsz, dtype=np.uint8)
         nblk = c_u32(0); scr = c_u64(0)
         first = np.zeros(self.n + 1, dtype=np.uint32); expect = np.zeros(max(self.n, 1), dtype=np.uint64)
@@ -246,6 +246,7 @@ class ZstdDeviceDecompressor:
             expect[i] = cs.value
         first[self.n] = nblk.value
         self.nblk = nblk.value
+        self.scan_ok = all(rc == 0 for rc in self.scan_status)
         oo = np.zeros(self.n + 1, dtype=np.int64); oo[1:] = np.cumsum(expect[: self.n].astype(np.int64))
         self.out_total = int(oo[-1])
         self.d_blocks = torch.from_numpy(blocks[: max(1, self.nblk) * dsz].copy()).to(device)
