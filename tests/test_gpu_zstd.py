@@ -86,6 +86,19 @@ def test_compress_roundtrip_through_reference(torch, kind, chunk):
     assert not status.any() and back.size == n and np.array_equal(back, src)
 
 
+@pytest.mark.parametrize("first", [2, 3, 4, 5, 6, 7])
+def test_every_data_class_roundtrips(torch, first):
+    """One chunk of every Silesia-mix class.  Class 6 (random) regression: a single stray 4-byte match inside an
+    otherwise incompressible window used to claim the whole window as its literal run."""
+    n = 1 << 20
+    src = z.gen_stream(z.GEN_MIX, n, 1 << 20, first=first)
+    framed, foff = gpu_compress(torch, src, 1 << 20)
+    rc, back = o.orc_decode(o.CODEC_ZSTD, framed, n)
+    assert rc == 0 and np.array_equal(back, src)
+    back, status, dec = gpu_decompress(torch, framed)
+    assert not status.any() and np.array_equal(back, src)
+
+
 def test_ratio_between_lz4_path_and_libzstd(torch):
     """Sanity: the entropy stage must buy something over the LZ4 container on text."""
     n = 8 << 20

@@ -74,6 +74,7 @@ struct __align__(16) CompressSmem {
     uint16_t hidx[C_MAXPIECE];            // piece index of the h-th head
     uint32_t longl[3 * (C_TILE / C_LONGLIT + 2)];
     // ---- end of tile arrays
+    ZFseShared fse;                       // zstd: predefined FSE encoding tables (unused by the LZ4 instantiation)
     uint32_t scanws[40];
     uint32_t nlong;
     uint32_t e_next;                      // chain state entering the next tile: position ...
@@ -81,7 +82,7 @@ struct __align__(16) CompressSmem {
     uint64_t mbar;
 };
 
-static_assert(offsetof(CompressSmem, scanws) - offsetof(CompressSmem, off) >= sizeof(ZEnt), "entropy scratch must fit in the tile arrays");
+static_assert(offsetof(CompressSmem, fse) - offsetof(CompressSmem, off) >= sizeof(ZEnt), "entropy scratch must fit in the tile arrays");
 
 // number of bytes (<= cap) for which s[p + i] == s[p + i - d]
 __device__ __forceinline__ uint32_t c_extend(const uint8_t* s, uint32_t p, uint32_t d, uint32_t cap)
@@ -189,6 +190,7 @@ lz77_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32_t c
     extern __shared__ __align__(16) uint8_t smem_raw[];
     CompressSmem& S = *reinterpret_cast<CompressSmem*>(smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (CODEC == 1) z_load_fse_shared(S.fse, tid, C_NT);
 
     for (uint32_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
         const uint32_t chunk = blk / bpc, bic = blk % bpc;
@@ -427,8 +429,8 @@ lz77_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32_t c
                     for (uint32_t i = tid; i < C - cover; i += C_NT) zs->lit[z_nlit + i] = S.in[cover + i];
                     const uint32_t nl = z_nlit + (C - cover);
                     CTA_SYNC();
-                    if (C > z_pos) out_pos += z_encode_block(ZE, zs, z_nseq, nl, S.in + z_pos, C - z_pos, false, dst + out_pos, S.scanws, cta_sync);
-                    z_pos = C; if (pd_valid) pd_lit = C;
+                    if (C > z_pos) out_pos += z_encode_block(ZE, S.fse, zs, z_nseq, nl, S.in + z_pos, C - z_pos, false, dst + out_pos, S.scanws, cta_sync);
+                    z_pos = C; pd_lit = C;                  // literals before C are emitted: the next sequence's literal run starts here
                     z_nseq = 0; z_nlit = 0;
                 }
             }
@@ -449,7 +451,7 @@ lz77_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32_t c
             z_nlit += n - anchor;
             CTA_SYNC();
             // the frame's last block carries the Last_Block bit; an empty raw block does when nothing is left
-            out_pos += z_encode_block(ZE, zs, z_nseq, z_nlit, S.in + z_pos, n - z_pos, z_last_of_chunk, dst + out_pos, S.scanws, cta_sync);
+            out_pos += z_encode_block(ZE, S.fse, zs, z_nseq, z_nlit, S.in + z_pos, n - z_pos, z_last_of_chunk, dst + out_pos, S.scanws, cta_sync);
             if (tid == 0) blk_csize[blk] = out_pos;
         } else {
             uint32_t anchor = 0;

@@ -44,6 +44,8 @@ struct ZEnt {
 
 // ---- predefined-distribution FSE encoding tables (filled by the host once per device: zstd_tables_init)
 struct ZFseCTable { uint16_t state[64]; int32_t dnb[64]; int32_t dfs[64]; uint32_t log; };
+// shared-memory copy used by the chain lanes (lane-divergent lookups would serialise in the constant cache)
+struct ZFseShared { uint16_t state[3][64]; int2 tt[3][64]; };      // tt = (deltaNbBits, deltaFindState); order LL, OF, ML
 __constant__ ZFseCTable c_fse_ll, c_fse_of, c_fse_ml;
 __constant__ uint8_t  c_ll_code[64], c_ml_code[128];
 __constant__ uint32_t c_ll_base[36], c_ml_base[53];
@@ -83,178 +85,247 @@ __device__ __forceinline__ void z_copy_out(uint8_t* dst, const uint32_t* buf, ui
 
 // Encode one block.  All 256 threads call it.  Returns (CTA-uniform) the bytes written at dst.
 //   seqs/nseq, lits/nlit : from the scratch;  raw/regen : the block's content in shared memory (raw fallback)
+__device__ __forceinline__ void z_load_fse_shared(ZFseShared& F, uint32_t tid, uint32_t nt)
+{
+    for (uint32_t i = tid; i < 3 * 64; i += nt) {
+        const uint32_t k = i >> 6, j = i & 63;
+        const ZFseCTable& T = k == 0 ? c_fse_ll : k == 1 ? c_fse_of : c_fse_ml;
+        F.state[k][j] = T.state[j]; F.tt[k][j] = make_int2(T.dnb[j], T.dfs[j]);
+    }
+}
+
+// named barrier for the 7 literal warps (224 threads); barrier 0 stays the CTA-wide one
+__device__ __forceinline__ void z_lit_sync() { __syncwarp(); asm volatile("bar.sync 1, 224;" ::: "memory"); }
+
+// exclusive scan over the 224 literal threads (7 warps); `ws` >= 9 words, double use protected by the leading barrier
+__device__ __forceinline__ uint32_t z_lit_exscan(uint32_t v, uint32_t* ws, uint32_t* total)
+{
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(ZMT_FULL_MASK, inc, d); if (lane >= (uint32_t)d) inc += y; }
+    z_lit_sync();
+    if (lane == 31) ws[wid] = inc;
+    z_lit_sync();
+    uint32_t base = 0, tot = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < 7; w++) { const uint32_t x = ws[w]; if (w < wid) base += x; tot += x; }
+    *total = tot;
+    return base + inc - v;
+}
+
+// Encode one block.  All 256 threads call it.  Returns (CTA-uniform) the bytes written at dst.
+//   seqs/nseq, lits/nlit : from the scratch;  raw/regen : the block's content in shared memory (raw fallback)
+// Warp 7 runs the three serial FSE state chains while warps 0..6 do the whole literal pipeline (histogram, Huffman
+// tree, canonical codes, 4 bit streams, literal section written to dst) behind their own named barrier.
 template <class SYNC>
-__device__ uint32_t z_encode_block(ZEnt& Z, ZScratch* zs, uint32_t nseq, uint32_t nlit, const uint8_t* raw, uint32_t regen,
+__device__ uint32_t z_encode_block(ZEnt& Z, const ZFseShared& F, ZScratch* zs, uint32_t nseq, uint32_t nlit, const uint8_t* raw, uint32_t regen,
                                    bool last, uint8_t* dst, uint32_t* scanws, SYNC cta_sync)
 {
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, NT = blockDim.x;
     const uint8_t* lits = zs->lit;
+    uint8_t* const p = dst + 3;                              // literals section starts right after the block header
 
-    // ------------------------------------------------------------ literal statistics
     Z.hist[tid] = 0;
     if (tid < 16) { Z.wcnt[tid] = 0; }
-    if (tid == 0) { Z.nused = 0; Z.maxsym = 0; Z.maxcnt = 0; Z.maxbits = 0; Z.mode = 0; }
+    if (tid == 0) { Z.nused = 0; Z.maxsym = 0; Z.maxcnt = 0; Z.maxbits = 0; Z.mode = 0; Z.seqbits = 0; }
+    for (uint32_t i = tid; i < Z_BITWORDS; i += NT) Z.bits[i] = 0;
     cta_sync();
-    for (uint32_t i = tid; i < nlit; i += NT) atomicAdd(&Z.hist[lits[i]], 1u);
-    cta_sync();
-    {
-        const uint32_t c = Z.hist[tid];
-        if (c) { atomicAdd(&Z.nused, 1u); atomicMax(&Z.maxsym, tid); atomicMax(&Z.maxcnt, c); }
-    }
-    cta_sync();
-    const uint32_t nused = Z.nused, maxsym = Z.maxsym;
-    // mode: 0 raw, 1 RLE, 2 Huffman
-    uint32_t lmode = 0;
-    if (nlit && Z.maxcnt == nlit) lmode = 1;
-    else if (nlit >= 64 && maxsym <= 128 && nused >= 2) lmode = 2;
 
-    // ------------------------------------------------------------ FSE state chains (warp 7, lanes 0..2) overlap the Huffman build
-    // Encoding order is last sequence first (RFC 8878 §3.1.1.3.2.1.1: the decoder reads backwards).
-    if (wid == 7 && lane < 3 && nseq) {
-        const ZFseCTable& T = lane == 0 ? c_fse_ll : lane == 1 ? c_fse_of : c_fse_ml;
-        auto code_of = [&](const ZSeq& q) -> uint32_t {
-            return lane == 0 ? z_ll_code(q.litlen) : lane == 1 ? z_highbit((uint32_t)q.off + 3u) : z_ml_code((uint32_t)q.mlen - 3u);
-        };
-        // init with the last sequence's symbol (FSE_initCState2): no bits emitted
-        uint32_t s = code_of(zs->seq[nseq - 1]);
-        uint32_t nbo = (uint32_t)(T.dnb[s] + (1 << 15)) >> 16;
-        uint32_t st = T.state[(((nbo << 16) - (uint32_t)T.dnb[s]) >> nbo) + T.dfs[s]];
-        zs->fse[lane][nseq - 1] = 0;
-        for (int i = (int)nseq - 2; i >= 0; i--) {
-            s = code_of(zs->seq[i]);
-            nbo = (st + (uint32_t)T.dnb[s]) >> 16;
-            zs->fse[lane][i] = (nbo << 16) | (st & ((1u << nbo) - 1));
-            st = T.state[(st >> nbo) + T.dfs[s]];
+    if (wid == 7) {
+        // ------------------------------------------------------------ FSE state chains
+        // Encoding order is last sequence first (RFC 8878 §3.1.1.3.2.1.1: the decoder reads backwards).  The chains are
+        // serial in the FSE state; everything else is off their critical path: the warp fetches 32 sequence records
+        // at a time (coalesced), every lane turns its record into the three symbol codes, the codes reach chain
+        // lanes 0 (LL), 1 (OF), 2 (ML) by shuffle one step ahead, tables sit in shared memory.
+        if (nseq) {
+            const uint32_t kk = lane < 3 ? lane : 0;
+            uint32_t st = 0;
+            for (int hi = (int)nseq - 1; hi >= 0; hi -= 32) {
+                const int idx = hi - (int)lane;              // lane 0 holds the record processed first
+                uint32_t packed = 0;
+                if (idx >= 0) {
+                    const ZSeq q = zs->seq[idx];
+                    packed = z_ll_code(q.litlen) | (z_highbit((uint32_t)q.off + 3u) << 8) | (z_ml_code((uint32_t)q.mlen - 3u) << 16);
+                }
+                const int cnt = hi + 1 < 32 ? hi + 1 : 32;
+                uint32_t pk = __shfl_sync(ZMT_FULL_MASK, packed, 0);
+                int2 tt = F.tt[kk][(pk >> (8 * kk)) & 0xFF];
+                for (int jj = 0; jj < cnt; jj++) {
+                    const int2 cur = tt;
+                    const uint32_t pkn = __shfl_sync(ZMT_FULL_MASK, packed, (jj + 1) & 31);      // next step's symbol + table entry
+                    tt = F.tt[kk][(pkn >> (8 * kk)) & 0xFF];
+                    if (lane < 3) {
+                        uint32_t outv = 0;
+                        if (hi == (int)nseq - 1 && jj == 0) {    // FSE_initCState2: start state from the last sequence's symbol, no bits
+                            const uint32_t nbo = (uint32_t)(cur.x + (1 << 15)) >> 16;
+                            st = F.state[kk][(((nbo << 16) - (uint32_t)cur.x) >> nbo) + cur.y];
+                        } else {
+                            const uint32_t nbo = (st + (uint32_t)cur.x) >> 16;
+                            outv = (nbo << 16) | (st & ((1u << nbo) - 1));
+                            st = F.state[kk][(st >> nbo) + cur.y];
+                        }
+                        zs->fse[kk][hi - jj] = outv;
+                    }
+                }
+            }
+            if (lane < 3) Z.fin[lane] = st;
         }
-        Z.fin[lane] = st;
-    }
-
-    // ------------------------------------------------------------ Huffman code lengths (direct-weight trees only: symbols 0..128)
-    if (lmode == 2) {
-        if (wid < 7) {
+    } else {
+        // ------------------------------------------------------------ literal pipeline (224 threads)
+        const uint32_t LT = 224;
+        for (uint32_t i = tid; i < nlit; i += LT) atomicAdd(&Z.hist[lits[i]], 1u);
+        z_lit_sync();
+        for (uint32_t s = tid; s < 256; s += LT) {
+            const uint32_t c = Z.hist[s];
+            Z.hlen[s] = 0;
+            if (c) { atomicAdd(&Z.nused, 1u); atomicMax(&Z.maxsym, s); atomicMax(&Z.maxcnt, c); }
+        }
+        z_lit_sync();
+        const uint32_t nused = Z.nused, maxsym = Z.maxsym;
+        uint32_t lmode = 0;                                  // 0 raw, 1 RLE, 2 Huffman (direct-weight trees only: symbols 0..128)
+        if (nlit && Z.maxcnt == nlit) lmode = 1;
+        else if (nlit >= 64 && maxsym <= 128 && nused >= 2) lmode = 2;
+        uint32_t tree_bytes = 0, lit_payload = 0, sbytes[4] = {0, 0, 0, 0}, swords[4] = {0, 0, 0, 0};
+        if (lmode == 2) {
             // order[]: present symbols by ascending (count, symbol)
-            for (uint32_t s = tid; s < 256; s += 7 * 32) {
+            for (uint32_t s = tid; s < 256; s += LT) {
                 const uint32_t c = Z.hist[s];
-                Z.hlen[s] = 0;
                 if (c) {
                     uint32_t r = 0;
                     for (uint32_t t = 0; t < 256; t++) { const uint32_t ct = Z.hist[t]; r += (ct && (ct < c || (ct == c && t < s))) ? 1u : 0u; }
                     Z.order[r] = (uint16_t)s;
                 }
             }
-        }
-    }
-    cta_sync();
-    if (lmode == 2 && tid == 0) {
-        // two-queue Huffman: leaves 0..nused-1 (ascending), internal nodes nused..2*nused-2
-        for (uint32_t i = 0; i < nused; i++) Z.ncnt[i] = Z.hist[Z.order[i]];
-        uint32_t li = 0, ii = nused, ni = nused;
-        for (uint32_t k = 0; k + 1 < nused; k++) {
-            uint32_t a, b;
-            if (li < nused && (ii >= ni || Z.ncnt[li] <= Z.ncnt[ii])) a = li++; else a = ii++;
-            if (li < nused && (ii >= ni || Z.ncnt[li] <= Z.ncnt[ii])) b = li++; else b = ii++;
-            Z.ncnt[ni] = Z.ncnt[a] + Z.ncnt[b]; Z.npar[a] = (uint16_t)ni; Z.npar[b] = (uint16_t)ni; ni++;
-        }
-        const uint32_t root = ni - 1;
-        // depths: reuse ncnt[] as depth (parents have larger indices)
-        Z.ncnt[root] = 0;
-        for (int v = (int)root - 1; v >= 0; v--) Z.ncnt[v] = Z.ncnt[Z.npar[v]] + 1;
-        uint32_t maxl = 0;
-        for (uint32_t i = 0; i < nused; i++) maxl = maxl > Z.ncnt[i] ? maxl : Z.ncnt[i];
-        if (maxl > Z_HUF_MAXBITS) {
-            // length-limit: clamp to 11, repay the Kraft excess by lengthening the longest shorter codes
-            // (leaf 0 = rarest = longest code), then hand back any overshoot by shortening 11-bit codes
-            int32_t excess = 0;                                  // in units of 2^-11
-            for (uint32_t i = 0; i < nused; i++) { if (Z.ncnt[i] > Z_HUF_MAXBITS) Z.ncnt[i] = Z_HUF_MAXBITS; excess += 1 << (Z_HUF_MAXBITS - Z.ncnt[i]); }
-            excess -= 1 << Z_HUF_MAXBITS;
-            while (excess > 0) {
-                int best = -1;
-                for (uint32_t i = 0; i < nused; i++)            // longest code below the limit whose step fits, else the longest one
-                    if (Z.ncnt[i] < Z_HUF_MAXBITS) { if (best < 0) best = (int)i; if ((1 << (Z_HUF_MAXBITS - 1 - Z.ncnt[i])) <= excess) { best = (int)i; break; } }
-                if (best < 0) break;
-                excess -= 1 << (Z_HUF_MAXBITS - 1 - Z.ncnt[best]);
-                Z.ncnt[best]++;
+            z_lit_sync();
+            if (tid == 0) {
+                // two-queue Huffman: leaves 0..nused-1 (ascending), internal nodes nused..2*nused-2
+                for (uint32_t i = 0; i < nused; i++) Z.ncnt[i] = Z.hist[Z.order[i]];
+                uint32_t li = 0, ii = nused, ni = nused;
+                for (uint32_t k = 0; k + 1 < nused; k++) {
+                    uint32_t a, b;
+                    if (li < nused && (ii >= ni || Z.ncnt[li] <= Z.ncnt[ii])) a = li++; else a = ii++;
+                    if (li < nused && (ii >= ni || Z.ncnt[li] <= Z.ncnt[ii])) b = li++; else b = ii++;
+                    Z.ncnt[ni] = Z.ncnt[a] + Z.ncnt[b]; Z.npar[a] = (uint16_t)ni; Z.npar[b] = (uint16_t)ni; ni++;
+                }
+                const uint32_t root = ni - 1;
+                Z.ncnt[root] = 0;                            // reuse ncnt[] as depth (parents have larger indices)
+                for (int v = (int)root - 1; v >= 0; v--) Z.ncnt[v] = Z.ncnt[Z.npar[v]] + 1;
+                uint32_t maxl = 0;
+                for (uint32_t i = 0; i < nused; i++) maxl = maxl > Z.ncnt[i] ? maxl : Z.ncnt[i];
+                if (maxl > Z_HUF_MAXBITS) {
+                    // length-limit: clamp to 11, repay the Kraft excess by lengthening the longest shorter codes
+                    // (leaf 0 = rarest = longest code), then hand back any overshoot by shortening 11-bit codes
+                    int32_t excess = 0;                      // in units of 2^-11
+                    for (uint32_t i = 0; i < nused; i++) { if (Z.ncnt[i] > Z_HUF_MAXBITS) Z.ncnt[i] = Z_HUF_MAXBITS; excess += 1 << (Z_HUF_MAXBITS - Z.ncnt[i]); }
+                    excess -= 1 << Z_HUF_MAXBITS;
+                    while (excess > 0) {
+                        int best = -1;
+                        for (uint32_t i = 0; i < nused; i++)
+                            if (Z.ncnt[i] < Z_HUF_MAXBITS) { if (best < 0) best = (int)i; if ((1 << (Z_HUF_MAXBITS - 1 - Z.ncnt[i])) <= excess) { best = (int)i; break; } }
+                        if (best < 0) break;
+                        excess -= 1 << (Z_HUF_MAXBITS - 1 - Z.ncnt[best]);
+                        Z.ncnt[best]++;
+                    }
+                    for (uint32_t i = 0; i < nused && excess < 0; i++)
+                        if (Z.ncnt[i] == Z_HUF_MAXBITS) { Z.ncnt[i]--; excess++; }
+                    maxl = Z_HUF_MAXBITS;
+                }
+                Z.maxbits = maxl;
+                for (uint32_t i = 0; i < nused; i++) Z.hlen[Z.order[i]] = (uint8_t)Z.ncnt[i];
             }
-            for (uint32_t i = 0; i < nused && excess < 0; i++)   // give back: 11 -> 10 costs one unit
-                if (Z.ncnt[i] == Z_HUF_MAXBITS) { Z.ncnt[i]--; excess++; }
-            maxl = Z_HUF_MAXBITS;
-        }
-        Z.maxbits = maxl;
-        for (uint32_t i = 0; i < nused; i++) Z.hlen[Z.order[i]] = (uint8_t)Z.ncnt[i];
-    }
-    cta_sync();
-    uint32_t lit_payload = 0, tree_bytes = 0;        // Huffman: bytes of the 4 streams / of the tree description
-    uint32_t per = 0;
-    if (lmode == 2) {
-        const uint32_t maxbits = Z.maxbits;
-        // canonical codes in the decoder's table order: ascending weight, then symbol
-        {
-            const uint32_t l = Z.hlen[tid];
-            if (l) atomicAdd(&Z.wcnt[maxbits + 1 - l], 1u);
-        }
-        cta_sync();
-        if (tid == 0) { uint32_t acc = 0; for (uint32_t w = 1; w <= maxbits; w++) { Z.wbase[w] = acc; acc += Z.wcnt[w] << (w - 1); } }
-        cta_sync();
-        {
-            const uint32_t l = Z.hlen[tid];
-            if (l) {
-                const uint32_t w = maxbits + 1 - l;
-                uint32_t r = 0;
-                for (uint32_t t = 0; t < tid; t++) r += (Z.hlen[t] == l) ? 1u : 0u;
-                Z.hcode[tid] = (uint16_t)((Z.wbase[w] + (r << (w - 1))) >> (w - 1));
+            z_lit_sync();
+            const uint32_t maxbits = Z.maxbits;
+            // canonical codes in the decoder's table order: ascending weight, then symbol
+            for (uint32_t s = tid; s < 256; s += LT) { const uint32_t l = Z.hlen[s]; if (l) atomicAdd(&Z.wcnt[maxbits + 1 - l], 1u); }
+            z_lit_sync();
+            if (tid == 0) { uint32_t acc = 0; for (uint32_t w = 1; w <= maxbits; w++) { Z.wbase[w] = acc; acc += Z.wcnt[w] << (w - 1); } }
+            z_lit_sync();
+            uint32_t mybitsum = 0;
+            for (uint32_t s = tid; s < 256; s += LT) {
+                const uint32_t l = Z.hlen[s];
+                if (l) {
+                    const uint32_t w = maxbits + 1 - l;
+                    uint32_t r = 0;
+                    for (uint32_t t = 0; t < s; t++) r += (Z.hlen[t] == l) ? 1u : 0u;
+                    Z.hcode[s] = (uint16_t)((Z.wbase[w] + (r << (w - 1))) >> (w - 1));
+                    mybitsum += Z.hist[s] * l;
+                }
             }
-        }
-        // estimated size: fall back to raw literals when Huffman does not pay
-        uint32_t est;
-        {
-            const uint32_t b = Z.hist[tid] * Z.hlen[tid];
-            uint32_t tot; (void)block_exscan(b, scanws, &tot);
+            uint32_t totbits;
+            (void)z_lit_exscan(mybitsum, scanws, &totbits);
             tree_bytes = 1 + (maxsym + 1) / 2;
-            est = (tot + 7) / 8 + 4 + tree_bytes + 6;
+            const uint32_t est = (totbits + 7) / 8 + 4 + tree_bytes + 6;
+            if (est >= nlit || est + 64 > Z_BITWORDS * 4) lmode = 0;       // Huffman does not pay (or would not fit the bit buffer)
         }
-        if (est >= nlit || est + 64 > Z_BITWORDS * 4) lmode = 0;
-    }
-
-    // ------------------------------------------------------------ literal streams (4 x 64 threads, contiguous runs, reverse bit order)
-    for (uint32_t i = tid; i < Z_BITWORDS; i += NT) Z.bits[i] = 0;
-    uint32_t sbytes[4] = {0, 0, 0, 0}, swords[4] = {0, 0, 0, 0};
-    if (lmode == 2) {
-        per = (nlit + 3) / 4;
-        const uint32_t k = tid >> 6, u = tid & 63;
-        const uint32_t s0 = k * per, s1 = (s0 + per < nlit) ? s0 + per : nlit;          // stream k covers [s0, s1)
-        const uint32_t cnt = s1 > s0 ? s1 - s0 : 0, g = (cnt + 63) / 64;
-        const uint32_t a = s0 + u * g < s1 ? s0 + u * g : s1, b = a + g < s1 ? a + g : s1;
-        uint32_t mybits = 0;
-        for (uint32_t i = a; i < b; i++) mybits += Z.hlen[lits[i]];
-        uint32_t tot;
-        const uint32_t pre = block_exscan(mybits, scanws, &tot);
-        if (u == 0) Z.sbits[k] = pre;                       // bits before stream k
-        if (tid == 0) Z.sbits[4] = tot;
-        cta_sync();
-        const uint32_t base_k = Z.sbits[k], end_k = k == 3 ? Z.sbits[4] : Z.sbits[k + 1];
-        uint32_t woff = 0;                                   // word offset of each stream's buffer
-        for (uint32_t q = 0; q < 4; q++) {
-            const uint32_t tq = (q == 3 ? Z.sbits[4] : Z.sbits[q + 1]) - Z.sbits[q];
-            sbytes[q] = tq / 8 + 1;
-            swords[q] = (tq + 32) / 32;
-            if (q < k) woff += swords[q];
+        uint32_t lit_hdr, lit_body;
+        if (lmode == 2) {
+            // 4 streams x 56 threads, contiguous runs, reverse bit order
+            const uint32_t per = (nlit + 3) / 4;
+            const uint32_t k = tid / 56, u = tid % 56;
+            const uint32_t s0 = k * per, s1 = (s0 + per < nlit) ? s0 + per : nlit;
+            const uint32_t cnt = s1 > s0 ? s1 - s0 : 0, g = (cnt + 55) / 56;
+            const uint32_t a = s0 + u * g < s1 ? s0 + u * g : s1, b = a + g < s1 ? a + g : s1;
+            uint32_t mybits = 0;
+            for (uint32_t i = a; i < b; i++) mybits += Z.hlen[lits[i]];
+            uint32_t tot;
+            const uint32_t pre = z_lit_exscan(mybits, scanws, &tot);
+            if (u == 0) Z.sbits[k] = pre;
+            if (tid == 0) Z.sbits[4] = tot;
+            z_lit_sync();
+            const uint32_t base_k = Z.sbits[k], end_k = k == 3 ? Z.sbits[4] : Z.sbits[k + 1];
+            uint32_t woff = 0;
+            for (uint32_t q = 0; q < 4; q++) {
+                const uint32_t tq = (q == 3 ? Z.sbits[4] : Z.sbits[q + 1]) - Z.sbits[q];
+                sbytes[q] = tq / 8 + 1; swords[q] = (tq + 32) / 32;
+                if (q < k) woff += swords[q];
+            }
+            const uint32_t pos_lo = end_k - (pre + mybits);      // my run sits after everything that FOLLOWS it in the stream
+            ZBitRun R; R.start(Z.bits + woff, pos_lo);
+            for (uint32_t i = b; i > a; i--) { const uint32_t sy = lits[i - 1]; R.add(Z.hcode[sy], Z.hlen[sy]); }
+            R.finish();
+            if (u == 0) z_put_bits(Z.bits + woff, end_k - base_k, 1, 1);     // end marker above the last symbol's code
+            lit_payload = sbytes[0] + sbytes[1] + sbytes[2] + sbytes[3];
+            lit_body = tree_bytes + 6 + lit_payload;
+            lit_hdr = (nlit < 1024 && lit_body < 1024) ? 3 : (nlit < 16384 && lit_body < 16384) ? 4 : 5;
+            z_lit_sync();
+            if (tid == 0) {
+                const uint32_t fmt = lit_hdr == 3 ? 1u : lit_hdr == 4 ? 2u : 3u;
+                const uint32_t nb = lit_hdr == 3 ? 10u : lit_hdr == 4 ? 14u : 18u;
+                const uint64_t v = 2ull | ((uint64_t)fmt << 2) | ((uint64_t)nlit << 4) | ((uint64_t)lit_body << (4 + nb));
+                for (uint32_t i = 0; i < lit_hdr; i++) p[i] = (uint8_t)(v >> (8 * i));
+                uint8_t* q = p + lit_hdr;
+                *q++ = (uint8_t)(127 + maxsym);             // direct weights for symbols 0 .. maxsym-1 (the last one is implied)
+                for (uint32_t s = 0; s < maxsym; s += 2) {
+                    const uint32_t w0 = Z.hlen[s] ? Z.maxbits + 1 - Z.hlen[s] : 0;
+                    const uint32_t w1 = (s + 1 < maxsym && Z.hlen[s + 1]) ? Z.maxbits + 1 - Z.hlen[s + 1] : 0;
+                    *q++ = (uint8_t)((w0 << 4) | w1);
+                }
+                q[0] = (uint8_t)sbytes[0]; q[1] = (uint8_t)(sbytes[0] >> 8); q[2] = (uint8_t)sbytes[1]; q[3] = (uint8_t)(sbytes[1] >> 8);
+                q[4] = (uint8_t)sbytes[2]; q[5] = (uint8_t)(sbytes[2] >> 8);
+            }
+            uint8_t* q = p + lit_hdr + tree_bytes + 6;
+            uint32_t wo = 0;
+            for (uint32_t kq = 0; kq < 4; kq++) { z_copy_out(q, Z.bits + wo, sbytes[kq], tid, LT); q += sbytes[kq]; wo += swords[kq]; }
+        } else {
+            lit_body = lmode == 1 ? 1 : nlit;
+            lit_hdr = nlit < 32 ? 1 : nlit < 4096 ? 2 : 3;
+            if (tid == 0) {
+                const uint32_t type = lmode;                  // 0 raw, 1 RLE
+                if (lit_hdr == 1) p[0] = (uint8_t)(type | (nlit << 3));
+                else if (lit_hdr == 2) { const uint32_t v = type | (1u << 2) | (nlit << 4); p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); }
+                else { const uint32_t v = type | (3u << 2) | (nlit << 4); p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); }
+                if (lmode == 1) p[lit_hdr] = lits[0];
+            }
+            if (lmode == 0) for (uint32_t i = tid; i < nlit; i += LT) p[lit_hdr + i] = lits[i];
         }
-        // my run's bits sit after everything that FOLLOWS it in the stream
-        const uint32_t pos_lo = end_k - (pre + mybits);
-        ZBitRun R; R.start(Z.bits + woff, pos_lo);
-        for (uint32_t i = b; i > a; i--) { const uint32_t s = lits[i - 1]; R.add(Z.hcode[s], Z.hlen[s]); }
-        R.finish();
-        if (u == 0) z_put_bits(Z.bits + woff, end_k - base_k, 1, 1);     // end marker above the last symbol's code
-        lit_payload = sbytes[0] + sbytes[1] + sbytes[2] + sbytes[3];
+        if (tid == 0) Z.seqbits = lit_hdr + lit_body;            // literals section size, for everyone after the join
     }
     cta_sync();
+    const uint32_t lit_total = Z.seqbits;
 
-    // ------------------------------------------------------------ section sizes
-    uint32_t lit_hdr, lit_body;
-    if (lmode == 2) { lit_body = tree_bytes + 6 + lit_payload; lit_hdr = (nlit < 1024 && lit_body < 1024) ? 3 : (nlit < 16384 && lit_body < 16384) ? 4 : 5; }
-    else if (lmode == 1) { lit_body = 1; lit_hdr = nlit < 32 ? 1 : nlit < 4096 ? 2 : 3; }
-    else { lit_body = nlit; lit_hdr = nlit < 32 ? 1 : nlit < 4096 ? 2 : 3; }
-    // sequence bit counts, in encoding order: index j = nseq-1-i
+    // ------------------------------------------------------------ sequences: bit counts in encoding order (index j = nseq-1-i)
+    for (uint32_t i = tid; i < Z_BITWORDS; i += NT) Z.bits[i] = 0;
     uint32_t seq_bits = 0, seq_pre = 0, my_cnt = 0, my_first = 0;
     if (nseq) {
         const uint32_t g = (nseq + NT - 1) / NT;
@@ -274,8 +345,9 @@ __device__ uint32_t z_encode_block(ZEnt& Z, ZScratch* zs, uint32_t nseq, uint32_
     }
     const uint32_t seq_hdr = nseq == 0 ? 1 : (nseq < 128 ? 2 : 3);        // nbSeq bytes (+ modes byte when nseq > 0)
     const uint32_t seq_body = nseq ? seq_bits / 8 + 1 : 0;
-    const uint32_t bsize = lit_hdr + lit_body + seq_hdr + seq_body;
+    const uint32_t bsize = lit_total + seq_hdr + seq_body;
     const bool use_raw = bsize >= regen || (seq_body + 8 > Z_BITWORDS * 4) || nseq >= 0x7F00;
+    cta_sync();
 
     // ------------------------------------------------------------ write
     if (use_raw) {
@@ -284,53 +356,15 @@ __device__ uint32_t z_encode_block(ZEnt& Z, ZScratch* zs, uint32_t nseq, uint32_
         cta_sync();
         return 3 + regen;
     }
-    uint8_t* p = dst + 3;
     if (tid == 0) {
         const uint32_t h = (bsize << 3) | (2u << 1) | (last ? 1u : 0u);
         dst[0] = (uint8_t)h; dst[1] = (uint8_t)(h >> 8); dst[2] = (uint8_t)(h >> 16);
-        // literals section header
-        if (lmode == 2) {
-            const uint32_t fmt = lit_hdr == 3 ? 1u : lit_hdr == 4 ? 2u : 3u;
-            const uint32_t nb = lit_hdr == 3 ? 10u : lit_hdr == 4 ? 14u : 18u;
-            const uint64_t v = 2ull | ((uint64_t)fmt << 2) | ((uint64_t)nlit << 4) | ((uint64_t)lit_body << (4 + nb));
-            for (uint32_t i = 0; i < lit_hdr; i++) p[i] = (uint8_t)(v >> (8 * i));
-            uint8_t* q = p + lit_hdr;
-            *q++ = (uint8_t)(127 + maxsym);                 // direct weights for symbols 0 .. maxsym-1 (the last one is implied)
-            for (uint32_t s = 0; s < maxsym; s += 2) {
-                const uint32_t w0 = Z.hlen[s] ? Z.maxbits + 1 - Z.hlen[s] : 0;
-                const uint32_t w1 = (s + 1 < maxsym && Z.hlen[s + 1]) ? Z.maxbits + 1 - Z.hlen[s + 1] : 0;
-                *q++ = (uint8_t)((w0 << 4) | w1);
-            }
-            q[0] = (uint8_t)sbytes[0]; q[1] = (uint8_t)(sbytes[0] >> 8); q[2] = (uint8_t)sbytes[1]; q[3] = (uint8_t)(sbytes[1] >> 8);
-            q[4] = (uint8_t)sbytes[2]; q[5] = (uint8_t)(sbytes[2] >> 8);
-        } else {
-            const uint32_t type = lmode;                      // 0 raw, 1 RLE
-            if (lit_hdr == 1) p[0] = (uint8_t)(type | (nlit << 3));
-            else if (lit_hdr == 2) { const uint32_t v = type | (1u << 2) | (nlit << 4); p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); }
-            else { const uint32_t v = type | (3u << 2) | (nlit << 4); p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); }
-            if (lmode == 1) p[lit_hdr] = lits[0];
-        }
-        // sequences section header
-        uint8_t* s = p + lit_hdr + lit_body;
+        uint8_t* s = p + lit_total;                            // sequences section header
         if (nseq == 0) s[0] = 0;
         else if (nseq < 128) { s[0] = (uint8_t)nseq; s[1] = 0; }
         else { s[0] = (uint8_t)((nseq >> 8) + 128); s[1] = (uint8_t)nseq; s[2] = 0; }
     }
-    if (lmode == 2) {
-        uint8_t* q = p + lit_hdr + tree_bytes + 6;
-        uint32_t woff = 0;
-        for (uint32_t k = 0; k < 4; k++) {
-            z_copy_out(q, Z.bits + woff, sbytes[k], tid, NT);
-            q += sbytes[k];
-            woff += swords[k];
-        }
-    } else if (lmode == 0) {
-        for (uint32_t i = tid; i < nlit; i += NT) p[lit_hdr + i] = lits[i];
-    }
-    cta_sync();
     if (nseq) {
-        for (uint32_t i = tid; i < Z_BITWORDS; i += NT) Z.bits[i] = 0;
-        cta_sync();
         ZBitRun R; R.start(Z.bits, seq_pre);
         for (uint32_t j = my_first; j < my_first + my_cnt; j++) {
             const uint32_t i = nseq - 1 - j;
@@ -352,7 +386,7 @@ __device__ uint32_t z_encode_block(ZEnt& Z, ZScratch* zs, uint32_t nseq, uint32_
             z_put_bits(Z.bits, pos, 1, 1);
         }
         cta_sync();
-        z_copy_out(p + lit_hdr + lit_body + seq_hdr, Z.bits, seq_body, tid, NT);
+        z_copy_out(p + lit_total + seq_hdr, Z.bits, seq_body, tid, NT);
     }
     cta_sync();
     return 3 + bsize;
