@@ -75,11 +75,12 @@ int      zmt_zstd_compress_device(const void* d_in, uint64_t in_bytes, uint32_t 
  * warp per block for sequence execution.  Descriptors are opaque (zmt_zstd_blk_desc_bytes() each). */
 size_t   zmt_zstd_blk_desc_bytes(void);
 int      zmt_zstd_scan_frame_host(const uint8_t* frame, size_t n, uint64_t base_off, uint32_t frame_idx, void* blocks_out,
-                                  uint32_t* nblocks_io, uint32_t max_blocks, uint64_t* scratch_used, uint64_t* content_size);
+                                  uint32_t* nblocks_io, uint32_t max_blocks, uint64_t* scratch_used, uint64_t* content_size,
+                                  uint32_t* needs_seq /* 1: blocks depend on earlier ones -> frame-sequential entropy pass */);
 size_t   zmt_zstdd_workspace_bytes(uint32_t nframes, uint32_t nblocks, uint64_t scratch_bytes);
 int      zmt_zstd_decompress_device(const void* d_in, const void* d_blocks, uint32_t nblocks, const uint32_t* d_frame_first_blk,
-                                    const uint64_t* d_expect, uint32_t nframes, void* d_out, const uint64_t* d_out_off,
-                                    uint64_t* d_out_size, uint32_t* d_status, void* d_work, void* stream);
+                                    const uint64_t* d_expect, const uint32_t* d_frame_seq, uint32_t nframes, void* d_out,
+                                    const uint64_t* d_out_off, uint64_t* d_out_size, uint32_t* d_status, void* d_work, void* stream);
 
 /* ---- per-kernel device timing (CUDA events on the launching stream) ----
  * zmt_prof_begin() arms it; every kernel launched by the entry points above is bracketed by two

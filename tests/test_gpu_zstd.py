@@ -108,23 +108,41 @@ def test_ratio_between_lz4_path_and_libzstd(torch):
     assert framed.size < 0.9 * lz4.size
 
 
-def test_decode_reports_unsupported_reference_streams(torch):
-    """libzstd's own frames need FSE-described tables / treeless literals: the B200 subset decoder
-    must say so per frame instead of producing wrong bytes (full-format decode is SURVEY §8(f) row 1)."""
+@pytest.mark.parametrize("level", [1, 3, 9, 19])
+@pytest.mark.parametrize("kind", [z.GEN_MIX, z.GEN_TEXT, z.GEN_RANDOM, z.GEN_ZEROS])
+def test_decode_reference_streams_bit_exact(torch, level, kind):
+    """libzstd's own frames (what zstd-mt / the reference CLI writes): FSE-described tables, FSE-coded Huffman weights,
+    treeless literals, repeat modes and repeat offsets — decoded by the frame-sequential entropy pass."""
     if not o.have_ref():
         pytest.skip("oracle/_ref not built")
-    src = z.gen_stream(z.GEN_TEXT, 2 << 20, 1 << 20)
-    rc, framed, st = o.ref_compress(o.CODEC_ZSTD, src, threads=2, level=3)
+    n, chunk = (6 << 20) + 999, 1 << 20
+    src = z.gen_stream(kind, n, chunk)
+    rc, framed, st = o.ref_compress(o.CODEC_ZSTD, src, threads=4, level=level, chunk=chunk)
     assert rc == 0
     back, status, dec = gpu_decompress(torch, framed)
-    assert all(s in (10,) for s in status.tolist())                # ZMT_ST_UNSUPPORTED
-    rc, _, _ = z.decompress_mem(z.CODEC_ZSTD, framed, src.size + 16)
-    assert z.lib().ZSTDCB_isError(rc)
-    # incompressible input makes libzstd emit raw blocks only: those decode
-    rnd = z.gen_stream(z.GEN_RANDOM, 2 << 20, 1 << 20)
-    rc, framed, st = o.ref_compress(o.CODEC_ZSTD, rnd, threads=2, level=3)
-    back, status, dec = gpu_decompress(torch, framed)
-    assert not status.any() and np.array_equal(back, rnd)
+    assert dec.scan_ok
+    assert not status.any(), status
+    assert back.size == n and np.array_equal(back, src)
+    # and through ZSTDCB_decompressDCtx with host buffers
+    rc, back2, st2 = z.decompress_mem(z.CODEC_ZSTD, framed, n + 16, threads=4)
+    assert rc == 0 and np.array_equal(back2, src)
+
+
+def test_decode_golden_fixtures(torch):
+    import json, os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    man = json.load(open(os.path.join(gold, "manifest.json")))
+    seen = 0
+    for case in man["cases"]:
+        if case["codec"] != "zstd":
+            continue
+        framed = np.fromfile(os.path.join(gold, case["file"]), dtype=np.uint8)
+        src = z.gen_stream(case["kind"], case["n"], case["chunk"], first=case["first"])
+        back, status, dec = gpu_decompress(torch, framed)
+        assert not status.any(), (case, status)
+        assert np.array_equal(back[: case["n"]], src), case
+        seen += 1
+    assert seen >= 3
 
 
 def test_decode_detects_corruption(torch):

@@ -68,10 +68,10 @@ def lib():
     L.zmt_zstd_compress_device.argtypes = [c_vp, c_u64, c_u32, c_vp, c_u32, c_vp, c_vp, c_vp, c_vp]
     L.zmt_zstd_blk_desc_bytes.restype = c_sz; L.zmt_zstd_blk_desc_bytes.argtypes = []
     L.zmt_zstd_scan_frame_host.restype = ctypes.c_int
-    L.zmt_zstd_scan_frame_host.argtypes = [c_vp, c_sz, c_u64, c_u32, c_vp, ctypes.POINTER(c_u32), c_u32, ctypes.POINTER(c_u64), ctypes.POINTER(c_u64)]
+    L.zmt_zstd_scan_frame_host.argtypes = [c_vp, c_sz, c_u64, c_u32, c_vp, ctypes.POINTER(c_u32), c_u32, ctypes.POINTER(c_u64), ctypes.POINTER(c_u64), ctypes.POINTER(c_u32)]
     L.zmt_zstdd_workspace_bytes.restype = c_sz; L.zmt_zstdd_workspace_bytes.argtypes = [c_u32, c_u32, c_u64]
     L.zmt_zstd_decompress_device.restype = ctypes.c_int
-    L.zmt_zstd_decompress_device.argtypes = [c_vp, c_vp, c_u32, c_vp, c_vp, c_u32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
+    L.zmt_zstd_decompress_device.argtypes = [c_vp, c_vp, c_u32, c_vp, c_vp, c_vp, c_u32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
     L.zmt_lz4d_workspace_bytes.restype = c_sz; L.zmt_lz4d_workspace_bytes.argtypes = [c_u32]
     L.zmt_lz4_decompress_device.restype = ctypes.c_int
     L.zmt_lz4_decompress_device.argtypes = [c_vp, c_u64, c_vp, c_vp, c_u32, c_u32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
@@ -236,14 +236,15 @@ class ZstdDeviceDecompressor:
         blocks = np.zeros(cap * dsz, dtype=np.uint8)
         nblk = c_u32(0); scr = c_u64(0)
         first = np.zeros(self.n + 1, dtype=np.uint32); expect = np.zeros(max(self.n, 1), dtype=np.uint64)
+        fseq = np.zeros(max(self.n, 1), dtype=np.uint32)
         self.scan_status = []
         for i in range(self.n):
             first[i] = nblk.value
-            cs = c_u64(0)
+            cs = c_u64(0); nsq = c_u32(0)
             rc = L.zmt_zstd_scan_frame_host(fb[int(offs[i]) + 12:].ctypes.data, int(sizes[i]), int(offs[i]) + 12, i, blocks.ctypes.data,
-                                            ctypes.byref(nblk), cap, ctypes.byref(scr), ctypes.byref(cs))
+                                            ctypes.byref(nblk), cap, ctypes.byref(scr), ctypes.byref(cs), ctypes.byref(nsq))
             self.scan_status.append(rc)
-            expect[i] = cs.value
+            expect[i] = cs.value; fseq[i] = nsq.value
         first[self.n] = nblk.value
         self.nblk = nblk.value
         self.scan_ok = all(rc == 0 for rc in self.scan_status)
@@ -252,6 +253,8 @@ class ZstdDeviceDecompressor:
         self.d_blocks = torch.from_numpy(blocks[: max(1, self.nblk) * dsz].copy()).to(device)
         self.d_first = torch.from_numpy(first.astype(np.int32)).to(device)
         self.d_expect = torch.from_numpy(expect.astype(np.int64)).to(device)
+        self.d_fseq = torch.from_numpy(fseq.astype(np.int32)).to(device)
+        self.n_seq_frames = int(fseq.sum())
         self.d_out_off = torch.from_numpy(oo).to(device)
         self.out = torch.empty(max(self.out_total, 1), dtype=torch.uint8, device=device)
         self.out_size = torch.zeros(max(self.n, 1), dtype=torch.int64, device=device)
@@ -262,7 +265,7 @@ class ZstdDeviceDecompressor:
         torch = _torch()
         s = stream if stream is not None else torch.cuda.current_stream()
         rc = lib().zmt_zstd_decompress_device(d_framed.data_ptr(), self.d_blocks.data_ptr(), self.nblk, self.d_first.data_ptr(), self.d_expect.data_ptr(),
-                                              self.n, self.out.data_ptr(), self.d_out_off.data_ptr(), self.out_size.data_ptr(), self.status.data_ptr(),
+                                              self.d_fseq.data_ptr(), self.n, self.out.data_ptr(), self.d_out_off.data_ptr(), self.out_size.data_ptr(), self.status.data_ptr(),
                                               self.work.data_ptr(), s.cuda_stream)
         if rc != 0:
             raise RuntimeError("zmt_zstd_decompress_device failed: %s" % ST_NAMES.get(rc, rc))

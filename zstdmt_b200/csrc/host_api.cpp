@@ -34,10 +34,11 @@ uint64_t zmt_zstdc_out_bound(uint32_t nchunks, uint32_t chunk_size);
 int      zmt_zstd_compress_device(const void*, uint64_t, uint32_t, const uint32_t*, uint32_t, void*, void*, uint64_t*, void*);
 size_t   zmt_zstd_blk_desc_bytes(void);
 int      zmt_zstd_scan_frame_host(const uint8_t* frame, size_t n, uint64_t base_off, uint32_t frame_idx, void* blocks_out, uint32_t* nblocks_io,
-                                  uint32_t max_blocks, uint64_t* scratch_used, uint64_t* content_size);
+                                  uint32_t max_blocks, uint64_t* scratch_used, uint64_t* content_size, uint32_t* needs_seq);
 size_t   zmt_zstdd_workspace_bytes(uint32_t nframes, uint32_t nblocks, uint64_t scratch_bytes);
 int      zmt_zstd_decompress_device(const void* d_in, const void* d_blocks, uint32_t nblocks, const uint32_t* d_frame_first_blk, const uint64_t* d_expect,
-                                    uint32_t nframes, void* d_out, const uint64_t* d_out_off, uint64_t* d_out_size, uint32_t* d_status, void* d_work, void* stream);
+                                    const uint32_t* d_frame_seq, uint32_t nframes, void* d_out, const uint64_t* d_out_off, uint64_t* d_out_size, uint32_t* d_status,
+                                    void* d_work, void* stream);
 }
 
 namespace {
@@ -540,10 +541,10 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
                 memcpy(s->h_in, carry.data(), carry.size());
                 T.a[0] = 0; T.d[0] = (uint32_t)(carry.size() - 12); T.b[0] = 0;
                 if (is_zstd) {
-                    uint64_t cs = 0; T.g[0] = 0;
-                    int zr = zmt_zstd_scan_frame_host(s->h_in + 12, carry.size() - 12, 12, 0, s->h_blk, &nblk, s->blk_cap, &scr, &cs);
+                    uint64_t cs = 0; uint32_t nsq = 0; T.g[0] = 0;
+                    int zr = zmt_zstd_scan_frame_host(s->h_in + 12, carry.size() - 12, 12, 0, s->h_blk, &nblk, s->blk_cap, &scr, &cs, &nsq);
                     if (zr != ZMT_ST_OK) { c->lib_errcode = (size_t)zr; P.fail(E.library); break; }
-                    T.f[0] = cs;
+                    T.f[0] = cs; T.d[0] = nsq;
                 }
                 in_used = carry.size(); out_used = carry_out; n = 1; carry.clear();
             }
@@ -576,11 +577,11 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
                 uint64_t osz = 0; bool okh = c->codec == CODEC_LZ4 ? lz4f_out_size(dstp + 12, toRead, c->frames + n, &osz) : zstd_out_size(dstp + 12, toRead, &osz);
                 if (!okh) { c->lib_errcode = ZMT_ST_BAD_HEADER; P.fail(c->codec == CODEC_LZ4 ? E.library : E.library); failed = true; break; }
                 if (to_carry) { carry_out = osz; break; }
-                uint32_t nblk_new = nblk; uint64_t scr_new = scr;
+                uint32_t nblk_new = nblk; uint64_t scr_new = scr; uint32_t nsq = 0;
                 if (is_zstd) {
                     // block table of this frame (descriptors are appended; rolled back if the frame moves to the next batch)
                     uint64_t cs = 0;
-                    int zr = zmt_zstd_scan_frame_host(dstp + 12, toRead, in_used + 12, n, s->h_blk, &nblk_new, s->blk_cap, &scr_new, &cs);
+                    int zr = zmt_zstd_scan_frame_host(dstp + 12, toRead, in_used + 12, n, s->h_blk, &nblk_new, s->blk_cap, &scr_new, &cs, &nsq);
                     if (zr == ZMT_ST_DST_SMALL && n > 0) { carry.assign(dstp, dstp + 12 + toRead); carry_out = osz; break; }
                     if (zr != ZMT_ST_OK) { c->lib_errcode = (size_t)zr; P.fail(zr == ZMT_ST_TRUNCATED || zr == ZMT_ST_TRAILING ? E.frame_decompress : E.library); failed = true; break; }
                     if (scr_new > scr_cap && n > 0) { carry.assign(dstp, dstp + 12 + toRead); carry_out = osz; break; }
@@ -596,13 +597,13 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
                         memcpy(s->h_in, save.data(), save.size());
                         if (is_zstd) {                     // the block table lived in the old slot: rebuild it
                             uint64_t cs = 0; nblk_new = 0; scr_new = 0;
-                            int zr = zmt_zstd_scan_frame_host(s->h_in + 12, toRead, 12, 0, s->h_blk, &nblk_new, s->blk_cap, &scr_new, &cs);
+                            int zr = zmt_zstd_scan_frame_host(s->h_in + 12, toRead, 12, 0, s->h_blk, &nblk_new, s->blk_cap, &scr_new, &cs, &nsq);
                             if (zr != ZMT_ST_OK) { c->lib_errcode = (size_t)zr; P.fail(E.library); failed = true; break; }
                         }
                     } else { carry.assign(dstp, dstp + 12 + toRead); carry_out = osz; break; }
                 }
                 T.a[n] = in_used; T.d[n] = (uint32_t)toRead; T.b[n] = out_used;
-                if (is_zstd) { T.g[n] = nblk; T.f[n] = osz; nblk = nblk_new; scr = scr_new; }
+                if (is_zstd) { T.g[n] = nblk; T.f[n] = osz; T.d[n] = nsq; nblk = nblk_new; scr = scr_new; }     // T.d doubles as the per-frame "needs sequential pass" flag
                 in_used += 12 + toRead; out_used += osz; n++;
             }
             if (failed) break;
@@ -669,7 +670,7 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
         if (ce == cudaSuccess) ce = cudaMemcpyAsync(s->d_tab, s->h_tab, s->tab_bytes, cudaMemcpyHostToDevice, s->stream);
         int st = ZMT_ST_CUDA;
         if (ce == cudaSuccess && is_zstd && s->nblk) ce = cudaMemcpyAsync(s->d_blk, s->h_blk, (size_t)s->nblk * zmt_zstd_blk_desc_bytes(), cudaMemcpyHostToDevice, s->stream);
-        if (ce == cudaSuccess) st = is_zstd ? zmt_zstd_decompress_device(s->d_in, s->d_blk, s->nblk, Td.g, Td.f, s->n, s->d_out, Td.b, Td.c, Td.e, s->d_work, s->stream)
+        if (ce == cudaSuccess) st = is_zstd ? zmt_zstd_decompress_device(s->d_in, s->d_blk, s->nblk, Td.g, Td.f, Td.d, s->n, s->d_out, Td.b, Td.c, Td.e, s->d_work, s->stream)
                                             : zmt_lz4_decompress_device(s->d_in, s->in_used, Td.a, Td.d, s->n, s->max_bpf, s->d_out, Td.b, Td.c, Td.e, s->d_work, s->stream);
         if (st == ZMT_ST_OK) {
             if (s->out_used) ce = cudaMemcpyAsync(s->h_out, s->d_out, s->out_used, cudaMemcpyDeviceToHost, s->stream);

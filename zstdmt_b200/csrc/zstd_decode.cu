@@ -2,18 +2,22 @@
 // /root/reference/lib/zstd-mt_decompress.c:442-527, one frame per 12-byte container header).
 //
 // Three kernels per batch, all block-parallel (a zstd frame of a 1 MiB chunk has ~64 blocks):
-//   zstd_entropy_kernel   one warp per block: literals (raw / RLE / Huffman with direct weights, 1 or 4 streams —
-//                         lanes 0..3 own the streams) and sequences (predefined FSE tables, lane 4) are decoded
+//   zstd_entropy_kernel   one warp per block (self-contained blocks: what our encoder emits): literals (raw / RLE /
+//                         Huffman, lanes 0..3 own the streams) and sequences (lane 0 walks the FSE states) are decoded
 //                         into per-block scratch; the block's regenerated size = literals + sum of match lengths
+//   zstd_entropy_seq_kernel  one warp per FRAME for frames whose blocks depend on earlier ones (treeless literals,
+//                         Repeat_Mode tables, repeat offsets — what libzstd emits for the reference): same routine,
+//                         blocks in order, state carried
 //   zstd_offsets_kernel   one thread per frame: exclusive scan of the regenerated sizes -> output offset per block,
 //                         content-size check against the frame header
 //   zstd_execute_kernel   one warp per block: literal / match copies in sequence order; a match that reaches below
 //                         the block's own output waits for the `done` flags of the blocks it reads from
 // Host side (zmt_zstd_scan_host): walks frame + block headers (3 bytes per block) and sizes the scratch.
 //
-// Scope: everything our encoder emits plus raw / RLE blocks and 1-stream literals.  Streams that need
-// FSE-described tables, FSE-coded Huffman weights, treeless literals or repeat offsets (what libzstd emits for the
-// reference) are reported per frame as ZMT_ST_UNSUPPORTED — never decoded on the CPU.
+// Scope: the full block format of RFC 8878 — raw / RLE / compressed blocks, Huffman literals with direct
+// or FSE-coded weights, 1 or 4 streams, treeless reuse, sequence tables predefined / RLE / FSE-described / repeat,
+// repeat offsets — i.e. what libzstd emits for the reference.  Not handled (reported per frame
+// as ZMT_ST_UNSUPPORTED, never decoded on the CPU): dictionaries, frames without a content size, XXH64 checksums.
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -74,27 +78,104 @@ struct BackBits {
 
 __device__ __forceinline__ void zd_fail(uint32_t* status, uint32_t f, uint32_t code) { atomicCAS(&status[f], 0u, code); }
 
-// ---------------------------------------------------------------- kernel 1: entropy decode
-#define ZD_WARPS 4
-__global__ void __launch_bounds__(32 * ZD_WARPS)
-zstd_entropy_kernel(const uint8_t* __restrict__ in, const ZBlk* __restrict__ blocks, uint32_t nblocks,
-                    uint8_t* __restrict__ scratch, uint32_t* __restrict__ regen, uint32_t* __restrict__ status)
-{
-    __shared__ uint16_t htab[ZD_WARPS][2048];            // (nbBits << 8) | symbol
-    __shared__ uint8_t  wts[ZD_WARPS][256];
-    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint32_t b = blockIdx.x * ZD_WARPS + wid;
-    if (b >= nblocks) return;
-    const ZBlk B = blocks[b];
-    if (B.type != ZB_CMP) { if (lane == 0) regen[b] = B.regen_hint; return; }
-    const uint8_t* src = in + B.comp_off;
-    const uint32_t n = B.comp_size;
-    uint8_t* lit = scratch + B.lit_off;
-    ZDSeq* seqs = reinterpret_cast<ZDSeq*>(scratch + B.seq_off);
-    uint16_t* T = htab[wid];
+// ---------------------------------------------------------------- per-warp decoding tables (shared memory)
+// FSE decode entry: base (16) | nbBits (8) << 16 | symbol << 24
+struct ZWarpTabs {
+    uint16_t huf[2048];            // (nbBits << 8) | symbol
+    uint32_t ll[512], of[256], ml[512];          // tables described in the stream (or RLE: 1 entry)
+    uint32_t pll[64], pof[32], pml[64];          // predefined tables
+    uint32_t wtab[64];             // FSE table of the Huffman weights (log <= 6)
+    uint8_t  wts[256];
+    int16_t  norm[64];
+    uint32_t hufbits;              // maxbits of the current Huffman table (0 = none yet)
+};
+#define ZD_NEEDS_SEQ 0x7Fu         // internal status: the frame needs the frame-sequential pass
 
+// Build an FSE decode table from normalized counts (RFC 8878 §4.1.1), one lane.
+__device__ bool zd_fse_build(uint32_t* tab, const int16_t* norm, int nsym, int log)
+{
+    const int size = 1 << log, step = (size >> 1) + (size >> 3) + 3;
+    int high = size - 1, pos = 0;
+    uint16_t next[64];
+    for (int s = 0; s < nsym; s++) { if (norm[s] == -1) { tab[high--] = (uint32_t)s << 24; next[s] = 1; } else next[s] = (uint16_t)norm[s]; }
+    for (int s = 0; s < nsym; s++)
+        for (int i = 0; i < norm[s]; i++) { tab[pos] = (uint32_t)s << 24; do { pos = (pos + step) & (size - 1); } while (pos > high); }
+    if (pos != 0) return false;
+    for (int i = 0; i < size; i++) {
+        const uint32_t sy = tab[i] >> 24;
+        const uint32_t x = next[sy]++;
+        const uint32_t nb = (uint32_t)log - (31 - __clz(x));
+        tab[i] = (sy << 24) | (nb << 16) | (((x << nb) - (uint32_t)size) & 0xFFFF);
+    }
+    return true;
+}
+
+// Normalized-count header, forward bit order (FSE_readNCount).  Returns bytes consumed or -1.
+__device__ int zd_read_ncount(const uint8_t* src, uint32_t n, int16_t* norm, int* nsym, int* log, int maxlog, int maxsym)
+{
+    uint32_t bitpos = 0;
+    auto peek = [&](uint32_t k) -> uint32_t {
+        const uint32_t b = bitpos >> 3; uint64_t v = 0;
+        for (uint32_t q = 0; q < 5; q++) if (b + q < n) v |= (uint64_t)src[b + q] << (8 * q);
+        return (uint32_t)(v >> (bitpos & 7)) & ((1u << k) - 1);
+    };
+    if (n < 1) return -1;
+    const int al = (int)peek(4) + 5; bitpos += 4;
+    if (al > maxlog) return -1;
+    int remaining = (1 << al) + 1, threshold = 1 << al, nbits = al + 1, sym = 0; bool prev0 = false;
+    for (int i = 0; i <= maxsym; i++) norm[i] = 0;
+    while (remaining > 1 && sym <= maxsym) {
+        if (prev0) {
+            for (;;) { const uint32_t rep = peek(2); bitpos += 2; sym += (int)rep; if (rep != 3) break; }
+            if (sym > maxsym + 1) return -1;
+            prev0 = false;
+            if (sym > maxsym) break;
+        }
+        const int max = (2 * threshold - 1) - remaining;
+        int count;
+        const uint32_t lo = peek((uint32_t)nbits - 1);
+        if ((int)lo < max) { count = (int)lo; bitpos += (uint32_t)nbits - 1; }
+        else { count = (int)peek((uint32_t)nbits); if (count >= threshold) count -= max; bitpos += (uint32_t)nbits; }
+        count--;
+        remaining -= count < 0 ? -count : count;
+        norm[sym++] = (int16_t)count;
+        prev0 = (count == 0);
+        while (remaining < threshold) { nbits--; threshold >>= 1; }
+    }
+    if (remaining != 1 || sym > maxsym + 1) return -1;
+    if (((bitpos + 7) >> 3) > n) return -1;
+    *nsym = sym; *log = al;
+    return (int)((bitpos + 7) >> 3);
+}
+
+// one of the three sequence tables for this block: mode 0 predefined, 1 RLE, 2 FSE-described, 3 repeat
+// cur = {table pointer, log}; returns false on error, sets *need_state when mode 3 cannot be honoured
+struct ZTabRef { const uint32_t* t; uint32_t log; };
+__device__ bool zd_seq_table(ZTabRef& cur, uint32_t mode, uint32_t* custom, const uint32_t* predef, uint32_t predef_log, int16_t* norm,
+                             const uint8_t*& qp, uint32_t& qn, int maxlog, int maxsym, bool have_prev, bool* need_state)
+{
+    if (mode == 0) { cur.t = predef; cur.log = predef_log; return true; }
+    if (mode == 1) { if (qn < 1 || qp[0] > maxsym) return false; custom[0] = (uint32_t)qp[0] << 24; cur.t = custom; cur.log = 0; qp++; qn--; return true; }
+    if (mode == 2) {
+        int nsym = 0, log = 0;
+        const int used = zd_read_ncount(qp, qn, norm, &nsym, &log, maxlog, maxsym);
+        if (used < 0) return false;
+        if (!zd_fse_build(custom, norm, nsym, log)) return false;
+        cur.t = custom; cur.log = (uint32_t)log; qp += used; qn -= (uint32_t)used; return true;
+    }
+    if (!have_prev) { *need_state = true; return false; }
+    return true;                                           // repeat: keep cur
+}
+
+// Decode one compressed block with one warp.  `fs` (frame state) carries tables + repeat offsets across blocks in the
+// frame-sequential pass; in the block-parallel pass fs == nullptr and anything that needs earlier blocks returns
+// ZD_NEEDS_SEQ.  Returns 0 ok / ZMT_ST_* / ZD_NEEDS_SEQ; *regen_out = regenerated bytes.
+struct ZFrameState { ZTabRef ll, of, ml; uint32_t rep[3]; bool have_tabs; };
+__device__ uint32_t zd_block(ZWarpTabs& W, const uint8_t* __restrict__ src, uint32_t n, const ZBlk& B, uint8_t* __restrict__ lit,
+                             ZDSeq* __restrict__ seqs, ZFrameState* fs, uint32_t* regen_out, uint32_t lane)
+{
     // ---- literals section
-    if (n < 1) { if (lane == 0) zd_fail(status, B.frame, ZMT_ST_BLOCK); return; }
+    if (n < 1) return ZMT_ST_BLOCK;
     const uint32_t b0 = src[0], ltype = b0 & 3, sf = (b0 >> 2) & 3;
     uint32_t lregen, lcomp = 0, lhdr, streams = 1;
     if (ltype < 2) {
@@ -103,65 +184,102 @@ zstd_entropy_kernel(const uint8_t* __restrict__ in, const ZBlk* __restrict__ blo
         else { lregen = (b0 >> 4) | ((uint32_t)src[1] << 4) | ((uint32_t)src[2] << 12); lhdr = 3; }
         lcomp = ltype == 0 ? lregen : 1;
     } else {
-        if (ltype == 3) { if (lane == 0) zd_fail(status, B.frame, ZMT_ST_UNSUPPORTED); return; }    // treeless literals
         if (sf < 2) { const uint32_t v = src[0] | (src[1] << 8) | ((uint32_t)src[2] << 16); lregen = (v >> 4) & 0x3FF; lcomp = (v >> 14) & 0x3FF; lhdr = 3; streams = sf == 0 ? 1 : 4; }
         else if (sf == 2) { const uint32_t v = ldg_le32(src); lregen = (v >> 4) & 0x3FFF; lcomp = (v >> 18) & 0x3FFF; lhdr = 4; streams = 4; }
         else { const uint64_t v = (uint64_t)ldg_le32(src) | ((uint64_t)src[4] << 32); lregen = (uint32_t)((v >> 4) & 0x3FFFF); lcomp = (uint32_t)((v >> 22) & 0x3FFFF); lhdr = 5; streams = 4; }
     }
-    if (lhdr + lcomp > n || lregen != B.regen_hint) { if (lane == 0) zd_fail(status, B.frame, ZMT_ST_BLOCK); return; }
+    if (lhdr + lcomp > n || lregen != B.regen_hint) return ZMT_ST_BLOCK;
     const uint8_t* lp = src + lhdr;
     if (ltype == 0) { for (uint32_t i = lane; i < lregen; i += 32) lit[i] = lp[i]; }
     else if (ltype == 1) { const uint8_t v = lp[0]; for (uint32_t i = lane; i < lregen; i += 32) lit[i] = v; }
     else {
-        // Huffman tree: direct 4-bit weights only
-        const uint32_t hb = lp[0];
-        if (hb < 128) { if (lane == 0) zd_fail(status, B.frame, ZMT_ST_UNSUPPORTED); return; }     // FSE-coded weights
-        const uint32_t nw = hb - 127, tbytes = 1 + (nw + 1) / 2;
-        if (tbytes + (streams == 4 ? 6u : 0u) > lcomp) { if (lane == 0) zd_fail(status, B.frame, ZMT_ST_BLOCK); return; }
-        uint32_t total = 0;
-        for (uint32_t i = lane; i < 256; i += 32) {
-            uint32_t w = 0;
-            if (i < nw) { const uint32_t by = lp[1 + i / 2]; w = (i & 1) ? (by & 15) : (by >> 4); }
-            wts[wid][i] = (uint8_t)w;
-            if (w) total += 1u << (w - 1);
-        }
+        uint32_t tbytes = 0;
+        if (ltype == 2) {
+            // ---- Huffman tree description: direct 4-bit weights, or weights coded with a small FSE table
+            const uint32_t hb = lp[0];
+            uint32_t nw;
+            if (hb >= 128) {
+                nw = hb - 127; tbytes = 1 + (nw + 1) / 2;
+                if (tbytes > lcomp) return ZMT_ST_BLOCK;
+                for (uint32_t i = lane; i < 256; i += 32) {
+                    uint32_t w = 0;
+                    if (i < nw) { const uint32_t by = lp[1 + i / 2]; w = (i & 1) ? (by & 15) : (by >> 4); }
+                    W.wts[i] = (uint8_t)w;
+                }
+            } else {
+                if (hb == 0 || 1 + hb > lcomp) return ZMT_ST_BLOCK;
+                tbytes = 1 + hb;
+                uint32_t cnt = 0;
+                if (lane == 0) {                                // serial: at most 255 weights
+                    int nsym = 0, log = 0; bool ok = true;
+                    const int hl = zd_read_ncount(lp + 1, hb, W.norm, &nsym, &log, 6, 15);
+                    BackBits R;
+                    if (hl < 0 || !zd_fse_build(W.wtab, W.norm, nsym, log) || !R.init(lp + 1 + hl, hb - (uint32_t)hl)) ok = false;
+                    if (ok) {
+                        uint32_t s1 = R.read((uint32_t)log), s2 = R.read((uint32_t)log);
+                        if (R.off < 0) ok = false;
+                        while (ok) {
+                            if (cnt >= 254) { ok = false; break; }
+                            uint32_t e = W.wtab[s1]; W.wts[cnt++] = (uint8_t)(e >> 24); s1 = (e & 0xFFFF) + R.read((e >> 16) & 0xFF);
+                            if (R.off < 0) { W.wts[cnt++] = (uint8_t)(W.wtab[s2] >> 24); break; }
+                            if (cnt >= 254) { ok = false; break; }
+                            e = W.wtab[s2]; W.wts[cnt++] = (uint8_t)(e >> 24); s2 = (e & 0xFFFF) + R.read((e >> 16) & 0xFF);
+                            if (R.off < 0) { W.wts[cnt++] = (uint8_t)(W.wtab[s1] >> 24); break; }
+                        }
+                    }
+                    if (!ok) cnt = 0xFFFFFFFFu;
+                }
+                cnt = __shfl_sync(ZMT_FULL_MASK, cnt, 0);
+                if (cnt == 0xFFFFFFFFu) return ZMT_ST_BLOCK;
+                nw = cnt;
+                __syncwarp();
+                for (uint32_t i = nw + lane; i < 256; i += 32) W.wts[i] = 0;
+            }
+            __syncwarp();
+            uint32_t total = 0;
+            for (uint32_t i = lane; i < nw; i += 32) { const uint32_t w = W.wts[i]; if (w > 11) total += 1u << 20; else if (w) total += 1u << (w - 1); }
 #pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) total += __shfl_xor_sync(ZMT_FULL_MASK, total, d);
-        if (total == 0 || total >= 2048) { if (lane == 0) zd_fail(status, B.frame, ZMT_ST_BLOCK); return; }
-        const uint32_t maxbits = 32 - __clz(total);       // highbit(total) + 1
-        const uint32_t left = (1u << maxbits) - total;
-        if (left == 0 || (left & (left - 1)) || maxbits > 11) { if (lane == 0) zd_fail(status, B.frame, ZMT_ST_BLOCK); return; }
-        __syncwarp();
-        if (lane == 0) wts[wid][nw] = (uint8_t)(32 - __clz(left));          // implied last weight = highbit(left) + 1
-        __syncwarp();
-        // table: ascending weight, then symbol order (RFC 8878 §4.2.1.3); lane owns symbols lane, lane+32, ...
-        // start index of symbol s = sum over (w' < w) cnt[w'] << (w'-1)  +  rank among equal weights << (w-1)
-        uint32_t cntw[12];
+            for (int d = 16; d >= 1; d >>= 1) total += __shfl_xor_sync(ZMT_FULL_MASK, total, d);
+            if (total == 0 || total >= 2048) return ZMT_ST_BLOCK;
+            const uint32_t maxbits = 32 - __clz(total);
+            const uint32_t left = (1u << maxbits) - total;
+            if (left == 0 || (left & (left - 1)) || maxbits > 11) return ZMT_ST_BLOCK;
+            if (lane == 0) W.wts[nw] = (uint8_t)(32 - __clz(left));
+            __syncwarp();
+            uint32_t cntw[12];
 #pragma unroll
-        for (int w = 0; w < 12; w++) cntw[w] = 0;
-        for (uint32_t s = 0; s <= nw; s++) { const uint32_t w = wts[wid][s]; if (w < 12) cntw[w]++; else cntw[0]++; }   // uniform loop, every lane
-        for (uint32_t s = lane; s <= nw; s += 32) {
-            const uint32_t w = wts[wid][s];
-            if (!w || w > 11) continue;
-            uint32_t start = 0;
-            for (uint32_t ww = 1; ww < w; ww++) start += cntw[ww] << (ww - 1);
-            uint32_t r = 0;
-            for (uint32_t t = 0; t < s; t++) r += wts[wid][t] == w ? 1u : 0u;
-            start += r << (w - 1);
-            const uint16_t e = (uint16_t)(((maxbits + 1 - w) << 8) | s);
-            for (uint32_t k = 0; k < (1u << (w - 1)); k++) T[start + k] = e;
+            for (int w = 0; w < 12; w++) cntw[w] = 0;
+            for (uint32_t s = 0; s <= nw; s++) { const uint32_t w = W.wts[s]; cntw[w < 12 ? w : 0]++; }
+            for (uint32_t s = lane; s <= nw; s += 32) {
+                const uint32_t w = W.wts[s];
+                if (!w || w > 11) continue;
+                uint32_t start = 0;
+                for (uint32_t ww = 1; ww < w; ww++) start += cntw[ww] << (ww - 1);
+                uint32_t r = 0;
+                for (uint32_t t = 0; t < s; t++) r += W.wts[t] == w ? 1u : 0u;
+                start += r << (w - 1);
+                const uint16_t e = (uint16_t)(((maxbits + 1 - w) << 8) | s);
+                for (uint32_t k = 0; k < (1u << (w - 1)); k++) W.huf[start + k] = e;
+            }
+            if (lane == 0) W.hufbits = maxbits;
+            __syncwarp();
+        } else {
+            // treeless: reuse the previous block's table (frame-sequential pass only)
+            if (!fs) return ZD_NEEDS_SEQ;
+            if (W.hufbits == 0) return ZMT_ST_BLOCK;
         }
-        __syncwarp();
+        const uint32_t maxbits = W.hufbits;
+        if (tbytes + (streams == 4 ? 6u : 0u) > lcomp) return ZMT_ST_BLOCK;
         const uint8_t* sp = lp + tbytes;
         uint32_t ssz[4], spos[4], per = lregen, nsym[4];
         if (streams == 4) {
             const uint32_t s1 = sp[0] | (sp[1] << 8), s2 = sp[2] | (sp[3] << 8), s3 = sp[4] | (sp[5] << 8);
             const uint32_t body = lcomp - tbytes - 6;
-            if (s1 + s2 + s3 > body) { if (lane == 0) zd_fail(status, B.frame, ZMT_ST_BLOCK); return; }
+            if (s1 + s2 + s3 > body) return ZMT_ST_BLOCK;
             ssz[0] = s1; ssz[1] = s2; ssz[2] = s3; ssz[3] = body - s1 - s2 - s3;
             spos[0] = 0; spos[1] = s1; spos[2] = s1 + s2; spos[3] = s1 + s2 + s3;
             per = (lregen + 3) / 4;
-            if (per * 3 > lregen) { if (lane == 0) zd_fail(status, B.frame, ZMT_ST_BLOCK); return; }
+            if (per * 3 > lregen) return ZMT_ST_BLOCK;
             nsym[0] = nsym[1] = nsym[2] = per; nsym[3] = lregen - 3 * per;
             sp += 6;
         } else { ssz[0] = lcomp - tbytes; spos[0] = 0; nsym[0] = lregen; ssz[1] = ssz[2] = ssz[3] = 0; spos[1] = spos[2] = spos[3] = 0; nsym[1] = nsym[2] = nsym[3] = 0; }
@@ -170,62 +288,155 @@ zstd_entropy_kernel(const uint8_t* __restrict__ in, const ZBlk* __restrict__ blo
             BackBits R;
             const uint32_t cnt = nsym[lane];
             uint8_t* o = lit + lane * per;
-            if (!R.init(sp + spos[lane], ssz[lane])) okh = (cnt == 0 && ssz[lane] == 0) ? false : false;
+            if (!R.init(sp + spos[lane], ssz[lane])) okh = false;
             else {
                 uint32_t st = R.read(maxbits);
                 for (uint32_t i = 0; i < cnt; i++) {
-                    const uint32_t e = T[st], nb = e >> 8;
+                    const uint32_t e = W.huf[st], nb = e >> 8;
                     o[i] = (uint8_t)e;
                     st = ((st << nb) & ((1u << maxbits) - 1)) | R.read(nb);
                 }
                 if (R.off != -(int32_t)maxbits) okh = false;
             }
         }
-        if (!__all_sync(ZMT_FULL_MASK, okh)) { if (lane == 0) zd_fail(status, B.frame, ZMT_ST_BLOCK); return; }
+        if (!__all_sync(ZMT_FULL_MASK, okh)) return ZMT_ST_BLOCK;
     }
 
-    // ---- sequences section (lane 0 walks the three interleaved FSE states; predefined tables only)
+    // ---- sequences section: lane 0 walks the three interleaved FSE states
     const uint8_t* qp = src + lhdr + lcomp;
     uint32_t qn = n - lhdr - lcomp;
-    uint32_t okq = 1, total_ml = 0;
+    uint32_t rc = 0, total_ml = 0;
     if (lane == 0) {
         do {
-            if (qn < 1) { okq = 0; break; }
+            if (qn < 1) { rc = ZMT_ST_BLOCK; break; }
             uint32_t nseq; const uint32_t q0 = qp[0];
             uint32_t used = 1;
             if (q0 == 0) nseq = 0;
             else if (q0 < 128) nseq = q0;
-            else if (q0 < 255) { if (qn < 2) { okq = 0; break; } nseq = ((q0 - 128) << 8) + qp[1]; used = 2; }
-            else { if (qn < 3) { okq = 0; break; } nseq = qp[1] + (qp[2] << 8) + 0x7F00; used = 3; }
-            if (nseq != B.nseq) { okq = 0; break; }
-            if (nseq == 0) { if (used != qn) okq = 0; break; }
-            if (qn < used + 1) { okq = 0; break; }
-            if (qp[used] != 0) { okq = 2; break; }                               // non-predefined table modes
-            used++;
+            else if (q0 < 255) { if (qn < 2) { rc = ZMT_ST_BLOCK; break; } nseq = ((q0 - 128) << 8) + qp[1]; used = 2; }
+            else { if (qn < 3) { rc = ZMT_ST_BLOCK; break; } nseq = qp[1] + (qp[2] << 8) + 0x7F00; used = 3; }
+            if (nseq != B.nseq) { rc = ZMT_ST_BLOCK; break; }
+            if (nseq == 0) { if (used != qn) rc = ZMT_ST_BLOCK; break; }
+            if (qn < used + 1) { rc = ZMT_ST_BLOCK; break; }
+            const uint32_t modes = qp[used];
+            if (modes & 3) { rc = ZMT_ST_BLOCK; break; }
+            qp += used + 1; qn -= used + 1;
+            ZTabRef tl, to, tm; bool need = false;
+            if (fs) { tl = fs->ll; to = fs->of; tm = fs->ml; } else { tl.t = to.t = tm.t = nullptr; tl.log = to.log = tm.log = 0; }
+            const bool hp = fs && fs->have_tabs;
+            if (!zd_seq_table(tl, (modes >> 6) & 3, W.ll, W.pll, 6, W.norm, qp, qn, 9, 35, hp, &need) ||
+                !zd_seq_table(to, (modes >> 4) & 3, W.of, W.pof, 5, W.norm, qp, qn, 8, 31, hp, &need) ||
+                !zd_seq_table(tm, (modes >> 2) & 3, W.ml, W.pml, 6, W.norm, qp, qn, 9, 52, hp, &need)) { rc = need ? ZD_NEEDS_SEQ : ZMT_ST_BLOCK; break; }
+            if (fs) { fs->ll = tl; fs->of = to; fs->ml = tm; fs->have_tabs = true; }
             BackBits R;
-            if (!R.init(qp + used, qn - used)) { okq = 0; break; }
-            uint32_t sLL = R.read(d_fse_ll.log), sOF = R.read(d_fse_of.log), sML = R.read(d_fse_ml.log);
+            if (!R.init(qp, qn)) { rc = ZMT_ST_BLOCK; break; }
+            uint32_t sLL = R.read(tl.log), sOF = R.read(to.log), sML = R.read(tm.log);
+            uint32_t r0 = fs ? fs->rep[0] : 1, r1 = fs ? fs->rep[1] : 4, r2 = fs ? fs->rep[2] : 8;
             for (uint32_t i = 0; i < nseq; i++) {
-                const uint32_t ofc = d_fse_of.sym[sOF], mlc = d_fse_ml.sym[sML], llc = d_fse_ll.sym[sLL];
-                if (ofc > 24) { okq = 0; break; }
-                const uint32_t ofv = (1u << ofc) + R.read(ofc);
+                const uint32_t eo = to.t[sOF], em = tm.t[sML], el = tl.t[sLL];
+                const uint32_t ofc = eo >> 24, mlc = em >> 24, llc = el >> 24;
+                if (ofc > 31 || mlc > 52 || llc > 35) { rc = ZMT_ST_BLOCK; break; }
+                uint32_t ofv = 1u << ofc;                         // offset codes above 25 do not occur below 32 MiB windows
+                if (ofc > 24) { ofv += R.read(ofc - 16) << 16; ofv += R.read(16); } else ofv += R.read(ofc);
                 const uint32_t ml = d_ml_base[mlc] + R.read(d_ml_bits[mlc]);
                 const uint32_t ll = d_ll_base[llc] + R.read(d_ll_bits[llc]);
-                if (ofv <= 3) { okq = 2; break; }                                 // repeat offsets: not in the B200 subset
-                if (i + 1 < nseq) {
-                    sLL = d_fse_ll.base[sLL] + R.read(d_fse_ll.nb[sLL]);
-                    sML = d_fse_ml.base[sML] + R.read(d_fse_ml.nb[sML]);
-                    sOF = d_fse_of.base[sOF] + R.read(d_fse_of.nb[sOF]);
+                uint32_t off;
+                if (ofv > 3) { off = ofv - 3; r2 = r1; r1 = r0; r0 = off; }
+                else {
+                    if (!fs) { rc = ZD_NEEDS_SEQ; break; }        // repeat offsets need the frame's history
+                    const uint32_t idx = ofv + (ll == 0 ? 1u : 0u);
+                    if (idx == 1) off = r0;
+                    else {
+                        off = idx == 4 ? r0 - 1 : (idx == 2 ? r1 : r2);
+                        if (off == 0) { rc = ZMT_ST_BLOCK; break; }
+                        if (idx > 2) r2 = r1;
+                        r1 = r0; r0 = off;
+                    }
                 }
-                if (R.off < 0) { okq = 0; break; }
-                ZDSeq q; q.ll = ll; q.off = ofv - 3; q.ml = ml; q.pad = 0;
+                if (i + 1 < nseq) {
+                    sLL = (el & 0xFFFF) + R.read((el >> 16) & 0xFF);
+                    sML = (em & 0xFFFF) + R.read((em >> 16) & 0xFF);
+                    sOF = (eo & 0xFFFF) + R.read((eo >> 16) & 0xFF);
+                }
+                if (R.off < 0) { rc = ZMT_ST_BLOCK; break; }
+                ZDSeq q; q.ll = ll; q.off = off; q.ml = ml; q.pad = 0;
                 seqs[i] = q;
                 total_ml += ml;
             }
-            if (okq == 1 && R.off != 0) okq = 0;
+            if (rc == 0 && R.off != 0) rc = ZMT_ST_BLOCK;
+            if (rc == 0 && fs) { fs->rep[0] = r0; fs->rep[1] = r1; fs->rep[2] = r2; }
         } while (0);
-        if (okq != 1) zd_fail(status, B.frame, okq == 2 ? ZMT_ST_UNSUPPORTED : ZMT_ST_BLOCK);
-        else regen[b] = lregen + total_ml;
+    }
+    rc = __shfl_sync(ZMT_FULL_MASK, rc, 0);
+    total_ml = __shfl_sync(ZMT_FULL_MASK, total_ml, 0);
+    *regen_out = lregen + total_ml;
+    return rc;
+}
+
+__device__ __forceinline__ void zd_load_predef(ZWarpTabs& W, uint32_t lane)
+{
+    for (uint32_t i = lane; i < 64; i += 32) {
+        W.pll[i] = ((uint32_t)d_fse_ll.sym[i] << 24) | ((uint32_t)d_fse_ll.nb[i] << 16) | d_fse_ll.base[i];
+        W.pml[i] = ((uint32_t)d_fse_ml.sym[i] << 24) | ((uint32_t)d_fse_ml.nb[i] << 16) | d_fse_ml.base[i];
+    }
+    W.pof[lane] = ((uint32_t)d_fse_of.sym[lane] << 24) | ((uint32_t)d_fse_of.nb[lane] << 16) | d_fse_of.base[lane];
+    if (lane == 0) W.hufbits = 0;
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------- kernel 1a: block-parallel entropy decode (self-contained blocks)
+#define ZD_WARPS 4
+__global__ void __launch_bounds__(32 * ZD_WARPS)
+zstd_entropy_kernel(const uint8_t* __restrict__ in, const ZBlk* __restrict__ blocks, uint32_t nblocks, const uint32_t* __restrict__ frame_seq,
+                    uint8_t* __restrict__ scratch, uint32_t* __restrict__ regen, uint32_t* __restrict__ status)
+{
+    __shared__ ZWarpTabs tabs[ZD_WARPS];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t b = blockIdx.x * ZD_WARPS + wid;
+    if (b >= nblocks) return;
+    const ZBlk B = blocks[b];
+    if (B.type != ZB_CMP) { if (lane == 0) regen[b] = B.regen_hint; return; }
+    if (frame_seq[B.frame]) return;                          // this frame goes through the frame-sequential pass
+    ZWarpTabs& W = tabs[wid];
+    zd_load_predef(W, lane);
+    uint32_t rg = 0;
+    const uint32_t rc = zd_block(W, in + B.comp_off, B.comp_size, B, scratch + B.lit_off, reinterpret_cast<ZDSeq*>(scratch + B.seq_off), nullptr, &rg, lane);
+    if (lane == 0) {
+        if (rc == 0) regen[b] = rg;
+        else if (rc == ZD_NEEDS_SEQ) atomicMax(&status[B.frame], ZD_NEEDS_SEQ | 0x8000u);      // flag (cleared by the sequential pass)
+        else zd_fail(status, B.frame, rc);
+    }
+}
+
+// ---------------------------------------------------------------- kernel 1b: frame-sequential entropy decode
+// One warp per frame that needs state across blocks: Huffman table reuse (treeless literals), Repeat_Mode sequence
+// tables, repeat offsets.  Same per-block routine, blocks in order, state in registers / this warp's shared tables.
+__global__ void __launch_bounds__(32 * ZD_WARPS)
+zstd_entropy_seq_kernel(const uint8_t* __restrict__ in, const ZBlk* __restrict__ blocks, const uint32_t* __restrict__ frame_first_blk,
+                        const uint32_t* __restrict__ frame_seq, uint8_t* __restrict__ scratch, uint32_t* __restrict__ regen,
+                        uint32_t* __restrict__ status, uint32_t nframes)
+{
+    __shared__ ZWarpTabs tabs[ZD_WARPS];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t f = blockIdx.x * ZD_WARPS + wid;
+    if (f >= nframes) return;
+    const uint32_t st0 = status[f];
+    const bool flagged = (st0 & 0x8000u) != 0;
+    if (!frame_seq[f] && !flagged) return;
+    __syncwarp();
+    if (lane == 0 && flagged) status[f] = 0;
+    ZWarpTabs& W = tabs[wid];
+    zd_load_predef(W, lane);
+    ZFrameState fs; fs.rep[0] = 1; fs.rep[1] = 4; fs.rep[2] = 8; fs.have_tabs = false;
+    fs.ll.t = fs.of.t = fs.ml.t = nullptr; fs.ll.log = fs.of.log = fs.ml.log = 0;
+    for (uint32_t b = frame_first_blk[f]; b < frame_first_blk[f + 1]; b++) {
+        const ZBlk B = blocks[b];
+        if (B.type != ZB_CMP) continue;                      // raw / RLE blocks: regen already set by kernel 1a
+        uint32_t rg = 0;
+        const uint32_t rc = zd_block(W, in + B.comp_off, B.comp_size, B, scratch + B.lit_off, reinterpret_cast<ZDSeq*>(scratch + B.seq_off), &fs, &rg, lane);
+        if (rc != 0) { if (lane == 0) zd_fail(status, f, rc == ZD_NEEDS_SEQ ? ZMT_ST_BLOCK : rc); return; }
+        if (lane == 0) regen[b] = rg;
+        __syncwarp();
     }
 }
 
@@ -355,8 +566,9 @@ static inline uint32_t h_rd32(const uint8_t* p) { return (uint32_t)p[0] | ((uint
 // Appends block descriptors (scratch offsets assigned from *scratch_used).  Returns ZMT_ST_*.
 extern "C" int zmt_zstd_scan_frame_host(const uint8_t* frame, size_t n, uint64_t base_off, uint32_t frame_idx,
                                         void* blocks_out, uint32_t* nblocks_io, uint32_t max_blocks,
-                                        uint64_t* scratch_used, uint64_t* content_size)
+                                        uint64_t* scratch_used, uint64_t* content_size, uint32_t* needs_seq)
 {
+    *needs_seq = 0;
     ZBlk* out = (ZBlk*)blocks_out;
     if (n < 6 || h_rd32(frame) != 0xFD2FB528u) return ZMT_ST_BAD_MAGIC;
     const uint32_t fhd = frame[4], fcs = fhd >> 6, single = (fhd >> 5) & 1, did = fhd & 3;
@@ -405,6 +617,13 @@ extern "C" int zmt_zstd_scan_frame_host(const uint8_t* frame, size_t n, uint64_t
             if (q0 == 0) nseq = 0; else if (q0 < 128) nseq = q0;
             else if (q0 < 255) { if (qn < 2) return ZMT_ST_BLOCK; nseq = ((q0 - 128) << 8) + q[1]; }
             else { if (qn < 3) return ZMT_ST_BLOCK; nseq = q[1] + (q[2] << 8) + 0x7F00; }
+            // state across blocks visible in the headers: treeless literals, FSE-coded weights are fine block-parallel,
+            // any non-predefined sequence table mode may be followed by Repeat_Mode -> frame-sequential pass
+            {
+                const uint32_t used = q0 == 0 ? 1u : q0 < 128 ? 1u : q0 < 255 ? 2u : 3u;
+                if (lt == 3) *needs_seq = 1;
+                if (nseq && qn > used && q[used] != 0) *needs_seq = 1;
+            }
             B.comp_size = bs; B.regen_hint = lregen; B.nseq = nseq;
             B.seq_off = *scratch_used; *scratch_used += (((uint64_t)nseq * sizeof(ZDSeq)) + 15) & ~15ull;
             B.lit_off = *scratch_used; *scratch_used += ((uint64_t)lregen + 15) & ~15ull;
@@ -429,7 +648,7 @@ extern "C" size_t zmt_zstdd_workspace_bytes(uint32_t nframes, uint32_t nblocks, 
 // d_blocks: nblocks descriptors (device copy of what zmt_zstd_scan_frame_host produced); d_frame_first_blk: nframes+1;
 // d_expect: content size per frame (from the frame headers)
 extern "C" int zmt_zstd_decompress_device(const void* d_in, const void* d_blocks, uint32_t nblocks, const uint32_t* d_frame_first_blk,
-                                          const uint64_t* d_expect, uint32_t nframes, void* d_out, const uint64_t* d_out_off,
+                                          const uint64_t* d_expect, const uint32_t* d_frame_seq, uint32_t nframes, void* d_out, const uint64_t* d_out_off,
                                           uint64_t* d_out_size, uint32_t* d_status, void* d_work, void* stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -445,7 +664,9 @@ extern "C" int zmt_zstd_decompress_device(const void* d_in, const void* d_blocks
     cudaMemsetAsync(regen, 0, (size_t)nblocks * 4, stream);
     cudaMemsetAsync(done, 0, (size_t)nblocks * 4, stream);
     if (nblocks) {
-        zstd_entropy_kernel<<<(nblocks + ZD_WARPS - 1) / ZD_WARPS, 32 * ZD_WARPS, 0, stream>>>((const uint8_t*)d_in, (const ZBlk*)d_blocks, nblocks, scratch, regen, d_status);
+        zstd_entropy_kernel<<<(nblocks + ZD_WARPS - 1) / ZD_WARPS, 32 * ZD_WARPS, 0, stream>>>((const uint8_t*)d_in, (const ZBlk*)d_blocks, nblocks, d_frame_seq, scratch, regen, d_status);
+        zstd_entropy_seq_kernel<<<(nframes + ZD_WARPS - 1) / ZD_WARPS, 32 * ZD_WARPS, 0, stream>>>((const uint8_t*)d_in, (const ZBlk*)d_blocks, d_frame_first_blk, d_frame_seq,
+                                                                                           scratch, regen, d_status, nframes);
     }
     zstd_offsets_kernel<<<(nframes + 127) / 128, 128, 0, stream>>>((const ZBlk*)d_blocks, nblocks, d_frame_first_blk, regen, blk_out, d_out_off, d_expect,
                                                                    (unsigned long long*)d_out_size, d_status, nframes);
