@@ -97,6 +97,16 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def traffic_per_launch(algorithmic_bytes):
+    """DRAM bytes per launch of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum of ONE ncu --set full
+    capture (profiles/r1_traffic.json, made at a smaller size), scaled by algorithmic bytes to this launch."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["lz4_compress_blocks_kernel"]
+        return float(t["dram_bytes"]) / float(t["algorithmic_bytes"]) * algorithmic_bytes
+    except Exception:
+        return None
+
+
 def algo_bytes_compress(in_bytes, framed_bytes):
     return in_bytes + framed_bytes
 
@@ -244,6 +254,33 @@ def run_b200(args):
         dms = e0.elapsed_time(e1) / args.steps
         extra["lz4_decompress_device_gbs"] = (n + framed) / (dms * 1e-3) / 1e9
         extra["lz4_decompress_ms_per_step"] = dms
+        # BASELINE config 3 class: decode of a stream framed by the REFERENCE (liblz4: linked blocks -> one warp per frame)
+        try:
+            import _oracle as o
+            if o.have_ref() and rank == 0:
+                rn = min(n, 1 << 30)
+                rc, rframed, rst = o.ref_compress(o.CODEC_LZ4, src[:rn], threads=min(os.cpu_count() or 1, 128), level=1, chunk=chunk)
+                assert rc == 0
+                roffs, rsizes = z.scan_frames(rframed)
+                rdec = z.Lz4DeviceDecompressor(roffs, rsizes, [chunk] * (rn // chunk))
+                d_rf = torch.from_numpy(rframed).cuda()
+                ro, rs = rdec.run(d_rf, stream); torch.cuda.synchronize()
+                assert int(rs.abs().sum().item()) == 0 and torch.equal(ro[:rn], d_in[:rn]), "decode of reference-framed stream mismatch"
+                for _ in range(2):
+                    rdec.run(d_rf, stream)
+                torch.cuda.synchronize()
+                e0.record(stream)
+                for _ in range(args.steps):
+                    rdec.run(d_rf, stream)
+                e1.record(stream); torch.cuda.synchronize()
+                rms = e0.elapsed_time(e1) / args.steps
+                extra["lz4_decompress_reference_frames_device_gbs"] = (rn + rframed.size) / (rms * 1e-3) / 1e9
+                extra["lz4_decompress_reference_frames_note"] = "%d MiB framed by the reference (liblz4 level 1, linked blocks): one warp per frame" % (rn >> 20)
+                del rdec, d_rf, ro
+        except AssertionError:
+            raise
+        except Exception as e:
+            extra["lz4_decompress_reference_frames_note"] = "skipped: %r" % (e,)
     del dec, dout
 
     # ---- end to end through the reference-shaped callback API (host buffers)
@@ -365,7 +402,7 @@ def run_b200(args):
         "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": n + 4 * nchunks, "d2h_bytes_per_step": outb + 8 * (nchunks + nchunks // 64 + 1),
                 "api": "LZ4MT_compressCCtx via in-memory fn_read/fn_write (csrc/memio_glue.c), threads=%d" % threads, "ms_per_step": e2e_s / args.steps * 1e3},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic_per_launch(algo_bytes_compress(n, framed)),
                      "kernel": "lz4_compress_blocks_kernel", "kernel_ms": kernel_ms, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo_bytes_compress(n, framed)},
         "extra": extra,

@@ -70,6 +70,7 @@ struct __align__(16) CompressSmem {
     uint16_t link[C_NT];                  // chain this chain merges into (C_END: leaves the tile)
     uint16_t jump[C_NT];
     uint8_t  reach[C_NT];
+    uint16_t entry[8];                    // per warp: first chain of the true path inside it (0xFFFF: none)
     uint16_t piece[C_MAXPIECE];           // tile-relative start of the r-th selected piece
     uint16_t hidx[C_MAXPIECE];            // piece index of the h-th head
     uint32_t longl[3 * (C_TILE / C_LONGLIT + 2)];
@@ -284,31 +285,41 @@ lz77_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32_t c
             CTA_SYNC();
             if (alive) c_walk<1>(S, tid, S.xfree[tid], S.xdin[tid], t0, limit);
             CTA_SYNC();
-            // ---------------- phase 3: reachability from k0 by pointer doubling
+            // ---------------- phase 3: which chains lie on the true path (entry k0, follow the links)
+            // Links only go forward.  Each warp resolves its own 32 chains with shuffles (pointer doubling on lane
+            // indices: terminal chain + bitmask of the lanes on the way), one thread then hops from warp to warp
+            // (<= 8 hops), and each warp reads its path mask back: 2 CTA barriers instead of 18.
+            bool on_path;
             {
                 const uint32_t lk = S.link[tid];
-                S.jump[tid] = (uint16_t)(lk == C_END ? tid : lk);
-                S.reach[tid] = (tid == k0);
+                const bool inwarp = (lk != C_END) && (lk != tid) && ((lk >> 5) == wid);
+                uint32_t jmp = inwarp ? (lk & 31) : lane;                 // next lane inside this warp (self = terminal)
+                uint32_t pm = (1u << lane) | (1u << jmp);
+#pragma unroll
+                for (int r = 0; r < 5; r++) { pm |= __shfl_sync(ZMT_FULL_MASK, pm, jmp); jmp = __shfl_sync(ZMT_FULL_MASK, jmp, jmp); }
+                S.jump[tid] = (uint16_t)(32 * wid + jmp);                  // terminal chain reached from tid without leaving the warp
+                S.xfree[tid] = pm;                                         // lanes on that way (xfree is dead after the continuation walk)
+                if (tid < 8) S.entry[tid] = 0xFFFFu;
                 CTA_SYNC();
-#pragma unroll 1
-                for (int r = 0; r < 8; r++) {
-                    const uint32_t j = S.jump[tid];
-                    const uint32_t rk = S.reach[tid];
-                    const uint32_t jj = S.jump[j];
-                    CTA_SYNC();
-                    if (rk) S.reach[j] = 1;
-                    S.jump[tid] = (uint16_t)jj;
-                    CTA_SYNC();
-                }
-                if (tid == k0) S.min_[tid] = e;
-                if (S.reach[tid]) {
-                    if (lk == C_END) { S.e_next = S.mpos[tid]; S.d_next = S.xdin[tid]; }
-                    else S.min_[lk] = S.mpos[tid];
+                if (tid == 0) {
+                    uint32_t cur = k0;
+                    S.min_[k0] = e;
+                    for (;;) {
+                        S.entry[cur >> 5] = (uint16_t)cur;
+                        const uint32_t t = S.jump[cur], tl = S.link[t];
+                        if (tl == C_END) { S.e_next = S.mpos[t]; S.d_next = S.xdin[t]; break; }
+                        S.min_[tl] = S.mpos[t];                            // entry position of the next warp's first chain on the path
+                        cur = tl;
+                    }
                 }
                 CTA_SYNC();
+                const uint32_t a = S.entry[wid];
+                on_path = (a != 0xFFFFu) && ((S.xfree[a] >> lane) & 1u);
+                if (on_path && inwarp) S.min_[lk] = S.mpos[tid];           // in-warp successor: entry position = my merge position
+                __syncwarp();
             }
             // ---------------- phase 4: mark the pieces of the true chain
-            if (S.reach[tid]) c_walk<2>(S, tid, S.min_[tid], tid == k0 ? e_din : 0u, t0, limit);
+            if (on_path) c_walk<2>(S, tid, S.min_[tid], tid == k0 ? e_din : 0u, t0, limit);
             CTA_SYNC();
             e = S.e_next; e_din = S.d_next;
 
@@ -316,7 +327,7 @@ lz77_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32_t c
             uint32_t np;
             {
                 uint32_t w = tid < C_TILE / 32 ? S.Sel[tid] : 0;
-                uint32_t base = block_exscan(__popc(w), S.scanws, &np);
+                uint32_t base = block_exscan1(__popc(w), S.scanws, 0, &np);
                 while (w) { const uint32_t b = __ffs(w) - 1; w &= w - 1; S.piece[base++] = (uint16_t)(tid * 32 + b); }
             }
             CTA_SYNC();
@@ -347,7 +358,7 @@ lz77_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32_t c
             }
             uint32_t nh;
             {
-                uint32_t hb = block_exscan(nh_local, S.scanws, &nh);
+                uint32_t hb = block_exscan1(nh_local, S.scanws, 1, &nh);
 #pragma unroll
                 for (uint32_t k = 0; k < PPT; k++) if (headmask & (1u << k)) S.hidx[hb++] = (uint16_t)(tid * PPT + k);
             }
@@ -378,7 +389,7 @@ lz77_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32_t c
                 }
             }
             uint32_t total;
-            uint32_t o = block_exscan(sz, S.scanws, &total);
+            uint32_t o = block_exscan1(sz, S.scanws, 0, &total);
             if (CODEC == 0) {
                 o += out_pos;
 #pragma unroll
