@@ -58,9 +58,15 @@ def build_oracle():
         raise RuntimeError("oracle build failed")
 
 
+def build_cli():
+    """Reference CLI (unmodified programs/main.c) linked against the product library — only where /root/reference exists."""
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "cli"], capture_output=True, text=True)
+
+
 def build_all(force=False, verbose=False):
     build_product(force=force, verbose=verbose)
     build_oracle()
+    build_cli()
 
 
 if __name__ == "__main__":
