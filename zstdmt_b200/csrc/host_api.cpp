@@ -35,6 +35,8 @@ int      zmt_zstd_compress_device(const void*, uint64_t, uint32_t, const uint32_
 size_t   zmt_zstd_blk_desc_bytes(void);
 int      zmt_zstd_scan_frame_host(const uint8_t* frame, size_t n, uint64_t base_off, uint32_t frame_idx, void* blocks_out, uint32_t* nblocks_io,
                                   uint32_t max_blocks, uint64_t* scratch_used, uint64_t* content_size, uint32_t* needs_seq);
+int      zmt_zstd_scan_frame_host2(const uint8_t* frame, size_t n, uint64_t base_off, uint32_t frame_idx, void* blocks_out, uint32_t* nblocks_io,
+                                   uint32_t max_blocks, uint64_t* scratch_used, uint64_t* content_size, uint32_t* needs_seq, size_t* consumed);
 size_t   zmt_zstdd_workspace_bytes(uint32_t nframes, uint32_t nblocks, uint64_t scratch_bytes);
 int      zmt_zstd_decompress_device(const void* d_in, const void* d_blocks, uint32_t nblocks, const uint32_t* d_frame_first_blk, const uint64_t* d_expect,
                                     const uint32_t* d_frame_seq, uint32_t nframes, void* d_out, const uint64_t* d_out_off, uint64_t* d_out_size, uint32_t* d_status,
@@ -448,6 +450,122 @@ size_t read_some(const ErrCodes& E, GenRdWr* rw, void* dst, size_t want, size_t*
     *got = b.size; return 0;
 }
 
+// ------------------------------------------------------------------ plain (unframed) single streams
+// What the reference routes to st_decompress (lz4-mt_decompress.c:391-483, zstd-mt_decompress.c:552-687): an ordinary
+// .lz4 / .zst file, i.e. codec frames back to back without the 12-byte size headers.  Frame lengths are only known after
+// walking the block headers, so this path is one-shot: read to EOF, scan on the host, decode everything on the GPU with
+// the same kernels, write.  `first`/`have` = the bytes already consumed by the stream-type sniffing.
+struct DevBuf { void* p = nullptr; ~DevBuf() { if (p) cudaFree(p); } bool alloc(size_t n) { return cudaMalloc(&p, n ? n : 1) == cudaSuccess; } };
+
+size_t decompress_single_stream(Ctx* c, GenRdWr* rw, const uint8_t* first, size_t have)
+{
+    const ErrCodes& E = *c->E;
+    const bool is_zstd = c->codec == CODEC_ZSTD;
+    std::vector<uint8_t> in(12, 0);                         // 12 pad bytes: the LZ4 kernel addresses a frame as base + off + 12
+    in.insert(in.end(), first, first + have);
+    size_t piece = c->inputsize < (64u << 10) ? (size_t)1 << 20 : c->inputsize;
+    for (;;) {
+        const size_t old = in.size();
+        in.resize(old + piece);
+        size_t got = 0;
+        size_t e = read_some(E, rw, in.data() + old, piece, &got);
+        in.resize(old + got);
+        if (e) return e;
+        if (got == 0) break;
+    }
+    const uint8_t* s = in.data() + 12; const size_t n = in.size() - 12;
+    c->insize = n;                                          // every byte of the stream, sniffed bytes included
+    // ---- host scan: frame table (+ zstd block table)
+    std::vector<uint64_t> foff, ooff(1, 0), expect; std::vector<uint32_t> fcs, first_blk(1, 0), fseq;
+    std::vector<uint8_t> blocks; uint32_t nblk = 0; uint64_t scratch = 0; uint32_t max_bpf = 1;
+    const size_t dsz = zmt_zstd_blk_desc_bytes();
+    if (is_zstd) blocks.resize((n / 3 + 16) * dsz);
+    size_t pos = 0;
+    while (pos < n) {
+        if (n - pos < 4) return E.data_error;
+        const uint32_t magic = rd32(s + pos);
+        if ((magic & 0xFFFFFFF0u) == 0x184D2A50u) {          // skippable frame: magic, LE32 size, payload
+            if (n - pos < 8 || n - pos - 8 < rd32(s + pos + 4)) return E.data_error;
+            pos += 8 + (size_t)rd32(s + pos + 4); continue;
+        }
+        if (!is_zstd) {
+            if (magic != LZ4F_MAGIC || n - pos < 7) return E.data_error;
+            const uint32_t flg = s[pos + 4], bd = s[pos + 5], id = (bd >> 4) & 7;
+            if ((flg >> 6) != 1 || id < 4) { c->lib_errcode = ZMT_ST_BAD_HEADER; return E.library; }
+            const uint64_t blkmax = 1ull << (8 + 2 * id);
+            size_t q = pos + 4 + 2 + ((flg & 8) ? 8 : 0) + ((flg & 1) ? 4 : 0) + 1;
+            uint64_t bound = 0;
+            for (;;) {
+                if (q + 4 > n) { c->lib_errcode = ZMT_ST_TRUNCATED; return E.frame_decompress; }
+                const uint32_t bh = rd32(s + q); q += 4;
+                if (bh == 0) break;
+                const uint32_t bs = bh & 0x7FFFFFFFu;
+                bound += (bh & 0x80000000u) ? bs : blkmax;
+                q += (size_t)bs + ((flg & 0x10) ? 4 : 0);
+            }
+            if (flg & 4) q += 4;
+            if (q > n) { c->lib_errcode = ZMT_ST_TRUNCATED; return E.frame_decompress; }
+            const uint64_t osz = (flg & 8) ? rd64(s + pos + 6) : bound;
+            foff.push_back(pos); fcs.push_back((uint32_t)(q - pos)); ooff.push_back(ooff.back() + osz);
+            const uint64_t nb = (osz + 65535) / 65536; if (nb > max_bpf) max_bpf = (uint32_t)(nb > 0xFFFFFFu ? 0xFFFFFFu : nb);
+            pos = q;
+        } else {
+            if (magic < 0xFD2FB522u || magic > 0xFD2FB528u) return E.data_error;
+            uint64_t cs = 0; uint32_t nsq = 0; size_t used = 0;
+            const int zr = zmt_zstd_scan_frame_host2(s + pos, n - pos, 12 + pos, (uint32_t)foff.size(), blocks.data(), &nblk, (uint32_t)(blocks.size() / dsz), &scratch, &cs, &nsq, &used);
+            if (zr != ZMT_ST_OK) { c->lib_errcode = (size_t)zr; return zr == ZMT_ST_TRUNCATED ? E.frame_decompress : E.library; }
+            foff.push_back(pos); expect.push_back(cs); fseq.push_back(nsq); first_blk.push_back(nblk); ooff.push_back(ooff.back() + cs);
+            pos += used;
+        }
+    }
+    const uint32_t nf = (uint32_t)foff.size();
+    if (nf == 0) return 0;
+    // ---- one-shot device decode
+    const std::vector<int> devs = env_devices();
+    if (devs.empty() || cudaSetDevice(devs[0]) != cudaSuccess) { c->lib_errcode = ZMT_ST_CUDA; return E.library; }
+    const uint64_t total = ooff.back();
+    DevBuf d_in, d_out, d_tab, d_blk, d_work;
+    const size_t tab_bytes = tables_bytes(nf);
+    std::vector<uint8_t> h_tab(tab_bytes);
+    Tables T = tables_at(h_tab.data(), nf);
+    for (uint32_t i = 0; i < nf; i++) { T.a[i] = foff[i]; T.b[i] = ooff[i]; if (is_zstd) { T.f[i] = expect[i]; T.d[i] = fseq[i]; T.g[i] = first_blk[i]; } else T.d[i] = fcs[i]; }
+    T.b[nf] = total; if (is_zstd) T.g[nf] = nblk;
+    const size_t wk = is_zstd ? zmt_zstdd_workspace_bytes(nf, nblk, scratch) : zmt_lz4d_workspace_bytes(nf);
+    if (!d_in.alloc(in.size() + 256) || !d_out.alloc(total + 256) || !d_tab.alloc(tab_bytes) || !d_work.alloc(wk) || (is_zstd && !d_blk.alloc((size_t)nblk * dsz))) { cudaGetLastError(); return E.mem; }
+    cudaStream_t st = nullptr;
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { c->lib_errcode = ZMT_ST_CUDA; return E.library; }
+    Tables Td = tables_at((uint8_t*)d_tab.p, nf);
+    cudaMemcpyAsync(d_in.p, in.data(), in.size(), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_tab.p, h_tab.data(), tab_bytes, cudaMemcpyHostToDevice, st);
+    if (is_zstd && nblk) cudaMemcpyAsync(d_blk.p, blocks.data(), (size_t)nblk * dsz, cudaMemcpyHostToDevice, st);
+    const int rc = is_zstd ? zmt_zstd_decompress_device(d_in.p, d_blk.p, nblk, Td.g, Td.f, Td.d, nf, d_out.p, Td.b, Td.c, Td.e, d_work.p, st)
+                           : zmt_lz4_decompress_device(d_in.p, in.size(), Td.a, Td.d, nf, max_bpf, d_out.p, Td.b, Td.c, Td.e, d_work.p, st);
+    std::vector<uint8_t> out(total ? total : 1);
+    std::vector<uint32_t> status(nf); std::vector<uint64_t> osz(nf);
+    cudaError_t ce = cudaSuccess;
+    if (rc == ZMT_ST_OK) {
+        if (total) ce = cudaMemcpyAsync(out.data(), d_out.p, total, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(status.data(), Td.e, (size_t)nf * 4, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(osz.data(), Td.c, (size_t)nf * 8, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    }
+    cudaStreamDestroy(st);
+    if (rc != ZMT_ST_OK || ce != cudaSuccess) { c->lib_errcode = ZMT_ST_CUDA; return E.library; }
+    for (uint32_t i = 0; i < nf; i++) {
+        if (status[i] != ZMT_ST_OK) { c->lib_errcode = status[i]; return (status[i] == ZMT_ST_TRUNCATED || status[i] == ZMT_ST_TRAILING) ? E.frame_decompress : E.library; }
+        // frame by frame, in pieces of at most `piece` bytes (st_decompress writes as it goes)
+        uint64_t o = 0;
+        while (o < osz[i]) {
+            GenBuffer b; b.buf = out.data() + ooff[i] + o; b.size = (size_t)((osz[i] - o) < piece ? (osz[i] - o) : piece); b.allocated = b.size;
+            const size_t want = b.size;
+            const int rv = rw->fn_write(rw->arg_write, &b);
+            if (rv != 0) return mt_error(E, rv);
+            c->outsize += b.size; o += want;
+        }
+    }
+    return 0;
+}
+
 size_t decompress_run(Ctx* c, GenRdWr* rw)
 {
     const ErrCodes& E = *c->E;
@@ -467,7 +585,7 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
         if (got != 4) return E.data_error;
         if (rd32(first) != MT_MAGIC_SKIPPABLE) {
             if (rd32(first) != LZ4F_MAGIC) return E.data_error;
-            c->lib_errcode = ZMT_ST_UNSUPPORTED; return E.library;     // plain .lz4 stream: SURVEY §8(f) row 2, not built yet
+            return decompress_single_stream(c, rw, first, 4);          // plain .lz4 stream (st_decompress, lz4-mt_decompress.c:512-520)
         }
         e = read_some(E, rw, first + 4, 8, &got); if (e) return e;
         if (got != 8) return E.read_fail;
@@ -480,7 +598,7 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
         if (have < 16) {
             if (have < 4 || !is_zstd(first)) return E.data_error;
             if (have == 9) return 0;                                   // empty file (zstd-mt_decompress.c:735-740)
-            c->lib_errcode = ZMT_ST_UNSUPPORTED; return E.library;     // plain zstd stream: §8(f) row 2
+            return decompress_single_stream(c, rw, first, have);       // short plain zstd stream
         }
         c->insize += 16;
         if (is_skip(first) && is_zstd(first + 12)) { hdr_pending = true; first_payload_have = 4; }          // pzstd style
@@ -489,7 +607,7 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
             size_t e2 = read_some(E, rw, tmp + 7, 5, &got); if (e2) return e2;
             if (got != 5) return E.data_error;
             c->insize += 5; memcpy(first, tmp, 12); hdr_pending = true; first_payload_have = 0;
-        } else if (is_zstd(first)) { c->lib_errcode = ZMT_ST_UNSUPPORTED; return E.library; }
+        } else if (is_zstd(first)) return decompress_single_stream(c, rw, first, have);    // plain .zst (zstd-mt_decompress.c:747-752)
         else return E.data_error;
     }
 

@@ -559,6 +559,9 @@ static int zd_tables_init()
     return ZMT_ST_OK;
 }
 
+extern "C" int zmt_zstd_scan_frame_host2(const uint8_t* frame, size_t n, uint64_t base_off, uint32_t frame_idx, void* blocks_out, uint32_t* nblocks_io,
+                                         uint32_t max_blocks, uint64_t* scratch_used, uint64_t* content_size, uint32_t* needs_seq, size_t* consumed);
+
 static inline uint32_t h_rd32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
 
 // Walk one zstd frame on the host (frame header + 3-byte block headers + the two section headers of every
@@ -567,6 +570,14 @@ static inline uint32_t h_rd32(const uint8_t* p) { return (uint32_t)p[0] | ((uint
 extern "C" int zmt_zstd_scan_frame_host(const uint8_t* frame, size_t n, uint64_t base_off, uint32_t frame_idx,
                                         void* blocks_out, uint32_t* nblocks_io, uint32_t max_blocks,
                                         uint64_t* scratch_used, uint64_t* content_size, uint32_t* needs_seq)
+{
+    return zmt_zstd_scan_frame_host2(frame, n, base_off, frame_idx, blocks_out, nblocks_io, max_blocks, scratch_used, content_size, needs_seq, nullptr);
+}
+
+// same, for frames whose length is not known in advance (plain .zst streams): *consumed receives the frame length
+extern "C" int zmt_zstd_scan_frame_host2(const uint8_t* frame, size_t n, uint64_t base_off, uint32_t frame_idx,
+                                         void* blocks_out, uint32_t* nblocks_io, uint32_t max_blocks,
+                                         uint64_t* scratch_used, uint64_t* content_size, uint32_t* needs_seq, size_t* consumed)
 {
     *needs_seq = 0;
     ZBlk* out = (ZBlk*)blocks_out;
@@ -633,6 +644,7 @@ extern "C" int zmt_zstd_scan_frame_host(const uint8_t* frame, size_t n, uint64_t
         first = false;
         if (last) break;
     }
+    if (consumed) { *consumed = pos; return ZMT_ST_OK; }
     return pos == n ? ZMT_ST_OK : ZMT_ST_TRAILING;
 }
 
