@@ -991,6 +991,16 @@ extern "C" int zmt_prof_end(double* ms, int* count, int max_ids)
     return ZMT_K_COUNT < max_ids ? ZMT_K_COUNT : max_ids;
 }
 
+// begin / end marks for code outside this file (zstd_decode.cu): same records as ZmtProfScope
+static cudaEvent_t g_mark_a[ZMT_K_COUNT];
+extern "C" void zmt_prof_mark(int id, void* stream, int end)
+{
+    if (!g_prof_on || id < 0 || id >= ZMT_K_COUNT) return;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!end) { cudaEventCreate(&g_mark_a[id]); cudaEventRecord(g_mark_a[id], st); }
+    else { cudaEvent_t b; cudaEventCreate(&b); cudaEventRecord(b, st); g_prof.push_back({id, g_mark_a[id], b}); }
+}
+
 static bool zmt_dbg_check(cudaStream_t st, const char* what)
 {
     static int on = -1;

@@ -25,6 +25,8 @@
 #include "common.cuh"
 #include "zmt_dev.h"
 
+extern "C" void zmt_prof_mark(int id, void* stream, int end);     // lz4_kernels.cu: record a begin / end event when profiling is armed
+
 // ---------------------------------------------------------------- block descriptors (host-built)
 #define ZB_RAW 0u
 #define ZB_RLE 1u
@@ -675,6 +677,7 @@ extern "C" int zmt_zstd_decompress_device(const void* d_in, const void* d_blocks
     cudaMemsetAsync(d_status, 0, (size_t)nframes * 4, stream);
     cudaMemsetAsync(regen, 0, (size_t)nblocks * 4, stream);
     cudaMemsetAsync(done, 0, (size_t)nblocks * 4, stream);
+    zmt_prof_mark(ZMT_K_ZSTD_DECODE, stream, 0);
     if (nblocks) {
         zstd_entropy_kernel<<<(nblocks + ZD_WARPS - 1) / ZD_WARPS, 32 * ZD_WARPS, 0, stream>>>((const uint8_t*)d_in, (const ZBlk*)d_blocks, nblocks, d_frame_seq, scratch, regen, d_status);
         zstd_entropy_seq_kernel<<<(nframes + ZD_WARPS - 1) / ZD_WARPS, 32 * ZD_WARPS, 0, stream>>>((const uint8_t*)d_in, (const ZBlk*)d_blocks, d_frame_first_blk, d_frame_seq,
@@ -686,5 +689,6 @@ extern "C" int zmt_zstd_decompress_device(const void* d_in, const void* d_blocks
         zstd_execute_kernel<<<(nblocks + ZX_WARPS - 1) / ZX_WARPS, 32 * ZX_WARPS, 0, stream>>>((const uint8_t*)d_in, (const ZBlk*)d_blocks, nblocks, scratch, regen, blk_out,
                                                                                            d_out_off, (uint8_t*)d_out, done, d_status);
     }
+    zmt_prof_mark(ZMT_K_ZSTD_DECODE, stream, 1);
     return cudaGetLastError() == cudaSuccess ? ZMT_ST_OK : ZMT_ST_CUDA;
 }
