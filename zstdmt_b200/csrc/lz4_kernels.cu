@@ -43,12 +43,13 @@ __device__ __forceinline__ uint64_t zmt_chunk_len(const uint32_t* __restrict__ c
 
 // ============================================================================ compressor
 #define LZ4_BLK      65536u
-#define C_NT         256u          // threads per CTA
+#define C_CHAINS     256u          // speculative chains per tile (one per 16-byte segment)
+#define C_NT         C_CHAINS      // smem arrays below are per chain
 #define C_TILE       4096u         // positions parsed per tile
 #define C_SEG        16u           // C_TILE / C_NT : positions owned by one speculative chain
 #define C_ROUND      1024u         // hash-table update granularity
 #define C_HASHLOG    12
-#define C_MAXPIECE   1280u         // max pieces per tile: 4096/4 match pieces + 256 continuation pieces
+#define C_MAXPIECE   1536u         // >= max pieces per tile (4096/4 match pieces + 256 continuation pieces), multiple of 512
 #define C_LONGLIT    32u           // literal runs longer than this are copied cooperatively
 #define C_END        0xFFFFu       // link: chain leaves the tile
 
@@ -76,7 +77,7 @@ struct __align__(16) CompressSmem {
     uint32_t longl[3 * (C_TILE / C_LONGLIT + 2)];
     // ---- end of tile arrays
     ZFseShared fse;                       // zstd: predefined FSE encoding tables (unused by the LZ4 instantiation)
-    uint32_t scanws[40];
+    uint32_t scanws[40];                  // block_exscan / block_exscan1 scratch (two 16-word halves + total)
     uint32_t nlong;
     uint32_t e_next;                      // chain state entering the next tile: position ...
     uint32_t d_next;                      // ... and offset of the match still open there (0 = free)
@@ -182,16 +183,19 @@ __device__ __forceinline__ uint32_t c_emit_seq(CompressSmem& S, uint8_t* dst, ui
 }
 
 // CODEC 0: LZ4 block format out.  CODEC 1: Zstandard blocks out (same candidates + parse, entropy stage per ~16 KiB).
-template <int CODEC>
-__global__ void __launch_bounds__(C_NT, 2)
+template <int CODEC, int NTHREADS>
+__global__ void __launch_bounds__(NTHREADS, 2)
 lz77_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32_t chunk_size, const uint32_t* __restrict__ chunk_bytes,
                    uint32_t bpc, uint8_t* __restrict__ tmp, uint32_t* __restrict__ blk_csize, uint32_t nblocks, uint32_t flags,
                    ZScratch* __restrict__ zscratch)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     CompressSmem& S = *reinterpret_cast<CompressSmem*>(smem_raw);
+    constexpr uint32_t NT = NTHREADS;                         // threads per CTA (chains stay C_CHAINS = 256)
+    static_assert(NT == 256 || NT == 512, "NT");
+    static_assert(CODEC == 0 || NT == 256, "the zstd entropy stage is written for 256 threads");
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (CODEC == 1) z_load_fse_shared(S.fse, tid, C_NT);
+    if (CODEC == 1) z_load_fse_shared(S.fse, tid, NT);
 
     for (uint32_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
         const uint32_t chunk = blk / bpc, bic = blk % bpc;
@@ -210,10 +214,10 @@ lz77_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32_t c
         if (tid == 0) { if (nb16) mbar_init(&S.mbar, 1); S.nlong = 0; }
         CTA_SYNC();
         if (tid == 0 && nb16) { mbar_expect_tx(&S.mbar, nb16); bulk_g2s(S.in, src, nb16, &S.mbar); }
-        for (uint32_t i = nb16 + tid; i < n; i += C_NT) S.in[i] = src[i];
-        for (uint32_t i = n + tid; i < ((n + 3) & ~3u) + 32 && i < LZ4_BLK + 32; i += C_NT) S.in[i] = 0;
+        for (uint32_t i = nb16 + tid; i < n; i += NT) S.in[i] = src[i];
+        for (uint32_t i = n + tid; i < ((n + 3) & ~3u) + 32 && i < LZ4_BLK + 32; i += NT) S.in[i] = 0;
         if (tid < 16) S.pad0[tid] = 0;
-        for (uint32_t i = tid; i < (1u << C_HASHLOG); i += C_NT) S.tab[i] = 0;
+        for (uint32_t i = tid; i < (1u << C_HASHLOG); i += NT) S.tab[i] = 0;
         // one thread observes the TMA completion; the CTA barrier publishes the staged bytes to everyone
         if (tid == 0 && nb16) { mbar_wait(&S.mbar, 0); asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&S.mbar))); }
         CTA_SYNC();
@@ -235,10 +239,11 @@ lz77_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32_t c
             uint32_t anyM = 0;
 #pragma unroll 1
             for (uint32_t r = 0; r < C_TILE / C_ROUND; r++) {
-                uint32_t hreg[4];
+                constexpr uint32_t KPR = C_ROUND / NT;       // positions per thread per round
+                uint32_t hreg[KPR];
 #pragma unroll
-                for (uint32_t k = 0; k < 4; k++) {
-                    const uint32_t rel = r * C_ROUND + k * C_NT + tid, i = t0 + rel;
+                for (uint32_t k = 0; k < KPR; k++) {
+                    const uint32_t rel = r * C_ROUND + k * NT + tid, i = t0 + rel;
                     const bool ok = (i + 12 <= n);
                     // 8-byte window: bytes i-4 .. i+3  (S.in is preceded by 16 pad bytes, so word -1 exists)
                     const uint32_t* w = reinterpret_cast<const uint32_t*>(S.in) + (i >> 2);
@@ -266,8 +271,8 @@ lz77_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32_t c
                 }
                 CTA_SYNC();
 #pragma unroll
-                for (uint32_t k = 0; k < 4; k++)
-                    if (hreg[k] != 0xFFFFFFFFu) atomicMax(&S.tab[hreg[k]], t0 + r * C_ROUND + k * C_NT + tid + 1);
+                for (uint32_t k = 0; k < KPR; k++)
+                    if (hreg[k] != 0xFFFFFFFFu) atomicMax(&S.tab[hreg[k]], t0 + r * C_ROUND + k * NT + tid + 1);
                 CTA_SYNC();
             }
             const uint32_t t1 = t0 + C_TILE;
@@ -279,9 +284,10 @@ lz77_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32_t c
             // ---------------- phase 2: speculative chains (own segment, then continuation)
             const uint32_t k0 = (e - t0) / C_SEG;
             const uint32_t seg0 = t0 + tid * C_SEG;
-            const bool alive = tid >= k0;
+            const bool is_chain = tid < C_CHAINS;          // threads beyond the chains only help in the data-parallel phases
+            const bool alive = is_chain && tid >= k0;
             if (alive) c_walk<0>(S, tid, tid == k0 ? e : seg0, tid == k0 ? e_din : 0u, t0, limit);
-            else S.link[tid] = (uint16_t)tid;             // dead: self link, never reached
+            else if (is_chain) S.link[tid] = (uint16_t)tid;   // dead: self link, never reached
             CTA_SYNC();
             if (alive) c_walk<1>(S, tid, S.xfree[tid], S.xdin[tid], t0, limit);
             CTA_SYNC();
@@ -291,14 +297,16 @@ lz77_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32_t c
             // (<= 8 hops), and each warp reads its path mask back: 2 CTA barriers instead of 18.
             bool on_path;
             {
-                const uint32_t lk = S.link[tid];
-                const bool inwarp = (lk != C_END) && (lk != tid) && ((lk >> 5) == wid);
+                const uint32_t lk = is_chain ? S.link[tid] : tid;
+                const bool inwarp = is_chain && (lk != C_END) && (lk != tid) && ((lk >> 5) == wid);
                 uint32_t jmp = inwarp ? (lk & 31) : lane;                 // next lane inside this warp (self = terminal)
                 uint32_t pm = (1u << lane) | (1u << jmp);
 #pragma unroll
                 for (int r = 0; r < 5; r++) { pm |= __shfl_sync(ZMT_FULL_MASK, pm, jmp); jmp = __shfl_sync(ZMT_FULL_MASK, jmp, jmp); }
-                S.jump[tid] = (uint16_t)(32 * wid + jmp);                  // terminal chain reached from tid without leaving the warp
-                S.xfree[tid] = pm;                                         // lanes on that way (xfree is dead after the continuation walk)
+                if (is_chain) {
+                    S.jump[tid] = (uint16_t)(32 * wid + jmp);              // terminal chain reached from tid without leaving the warp
+                    S.xfree[tid] = pm;                                     // lanes on that way (xfree is dead after the continuation walk)
+                }
                 if (tid < 8) S.entry[tid] = 0xFFFFu;
                 CTA_SYNC();
                 if (tid == 0) {
@@ -313,7 +321,7 @@ lz77_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32_t c
                     }
                 }
                 CTA_SYNC();
-                const uint32_t a = S.entry[wid];
+                const uint32_t a = is_chain ? S.entry[wid] : 0xFFFFu;
                 on_path = (a != 0xFFFFu) && ((S.xfree[a] >> lane) & 1u);
                 if (on_path && inwarp) S.min_[lk] = S.mpos[tid];           // in-warp successor: entry position = my merge position
                 __syncwarp();
@@ -335,7 +343,7 @@ lz77_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32_t c
             // piece r is a HEAD unless it continues the previous piece's match: flagged continuation, or contiguous with the
             // same offset (the effective offset of a flagged piece is that of the nearest unflagged piece before it)
             uint32_t nh_local = 0, headmask = 0;
-            constexpr uint32_t PPT = C_MAXPIECE / C_NT;   // pieces per thread
+            constexpr uint32_t PPT = C_MAXPIECE / NT;     // pieces per thread
 #pragma unroll
             for (uint32_t k = 0; k < PPT; k++) {
                 const uint32_t r = tid * PPT + k;
@@ -369,10 +377,11 @@ lz77_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32_t c
             if (pd_valid && S.hidx[0] > 0) { const uint32_t pb = S.piece[S.hidx[0] - 1]; pd_end = t0 + pb + S.len[pb]; }
             // sequences to emit now: [pending] + heads 0 .. nh-2 ; head nh-1 becomes the new pending sequence
             const uint32_t nemit = pd_valid + nh - 1;
-            uint32_t sz = 0, e_lit0[4], e_lit[4], e_off[4], e_len[4], cnt = 0;
+            constexpr uint32_t SPT = 1024 / NT;           // sequences per thread (at most 1024 per tile)
+            uint32_t sz = 0, e_lit0[SPT], e_lit[SPT], e_off[SPT], e_len[SPT], cnt = 0;
 #pragma unroll
-            for (uint32_t k = 0; k < 4; k++) {
-                const uint32_t sidx = tid * 4 + k;
+            for (uint32_t k = 0; k < SPT; k++) {
+                const uint32_t sidx = tid * SPT + k;
                 if (sidx < nemit) {
                     uint32_t ls, st, of, en;
                     if (pd_valid && sidx == 0) { ls = pd_lit; st = pd_start; of = pd_off; en = pd_end; }
@@ -393,14 +402,14 @@ lz77_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32_t c
             if (CODEC == 0) {
                 o += out_pos;
 #pragma unroll
-                for (uint32_t k = 0; k < 4; k++) {
+                for (uint32_t k = 0; k < SPT; k++) {
                     if (k >= cnt) break;
                     o += c_emit_seq(S, dst, o, e_lit0[k], e_lit[k], e_off[k], e_len[k]);
                 }
             } else {
                 uint32_t si = z_nseq + (o >> 18), li = z_nlit + (o & 0x3FFFF);
 #pragma unroll
-                for (uint32_t k = 0; k < 4; k++) {
+                for (uint32_t k = 0; k < SPT; k++) {
                     if (k >= cnt) break;
                     ZSeq q; q.litlen = e_lit[k]; q.off = (uint16_t)e_off[k]; q.mlen = (uint16_t)e_len[k];
                     zs->seq[si++] = q;
@@ -413,7 +422,7 @@ lz77_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32_t c
             {   // cooperative copies of long literal runs: one warp per run
                 const uint32_t nl = S.nlong;
                 uint8_t* const ldst = CODEC == 0 ? dst : zs->lit;
-                for (uint32_t s = wid; s < nl; s += C_NT / 32) {
+                for (uint32_t s = wid; s < nl; s += NT / 32) {
                     const uint32_t sp = S.longl[3 * s], dp = S.longl[3 * s + 1], ln = S.longl[3 * s + 2];
                     for (uint32_t i = lane; i < ln; i += 32) ldst[dp + i] = S.in[sp + i];
                 }
@@ -437,7 +446,7 @@ lz77_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32_t c
                     // trailing literals up to C: everything before the pending match (or all parsed bytes when nothing is pending)
                     const uint32_t cover = pd_valid ? pd_lit : z_pos;
                     const uint32_t C = pd_valid ? pd_start : t1;
-                    for (uint32_t i = tid; i < C - cover; i += C_NT) zs->lit[z_nlit + i] = S.in[cover + i];
+                    for (uint32_t i = tid; i < C - cover; i += NT) zs->lit[z_nlit + i] = S.in[cover + i];
                     const uint32_t nl = z_nlit + (C - cover);
                     CTA_SYNC();
                     if (C > z_pos) out_pos += z_encode_block(ZE, S.fse, zs, z_nseq, nl, S.in + z_pos, C - z_pos, false, dst + out_pos, S.scanws, cta_sync);
@@ -455,10 +464,10 @@ lz77_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32_t c
                 anchor = pd_end;
                 const uint32_t ll = pd_start - pd_lit;
                 if (tid == 0) { ZSeq q; q.litlen = ll; q.off = (uint16_t)pd_off; q.mlen = (uint16_t)(pd_end - pd_start); zs->seq[z_nseq] = q; }
-                for (uint32_t i = tid; i < ll; i += C_NT) zs->lit[z_nlit + i] = S.in[pd_lit + i];
+                for (uint32_t i = tid; i < ll; i += NT) zs->lit[z_nlit + i] = S.in[pd_lit + i];
                 z_nseq++; z_nlit += ll;
             }
-            for (uint32_t i = tid; i < n - anchor; i += C_NT) zs->lit[z_nlit + i] = S.in[anchor + i];
+            for (uint32_t i = tid; i < n - anchor; i += NT) zs->lit[z_nlit + i] = S.in[anchor + i];
             z_nlit += n - anchor;
             CTA_SYNC();
             // the frame's last block carries the Last_Block bit; an empty raw block does when nothing is left
@@ -473,7 +482,7 @@ lz77_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32_t c
                 CTA_SYNC();
                 if (S.nlong) {                              // its literal run was long: copy it with the whole CTA
                     const uint32_t sp = S.longl[0], dp = S.longl[1], ln = S.longl[2];
-                    for (uint32_t i = tid; i < ln; i += C_NT) dst[dp + i] = S.in[sp + i];
+                    for (uint32_t i = tid; i < ln; i += NT) dst[dp + i] = S.in[sp + i];
                 }
             }
             const uint32_t lit = n - anchor;
@@ -489,7 +498,7 @@ lz77_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32_t c
                     if (lit >= 15) { uint32_t x = lit - 15; while (x >= 255) { *q++ = 255; x -= 255; } *q++ = (uint8_t)x; }
                     blk_csize[blk] = fin;
                 }
-                for (uint32_t i = tid; i < lit; i += C_NT) op[hl + i] = S.in[anchor + i];
+                for (uint32_t i = tid; i < lit; i += NT) op[hl + i] = S.in[anchor + i];
             }
         }
     }
@@ -1061,11 +1070,17 @@ extern "C" int zmt_lz4_compress_device(const void* d_in, uint64_t in_bytes, uint
     uint32_t* chk = (uint32_t*)w; w += (((uint64_t)nchunks * 4 + 255) & ~255ull);
     uint64_t* frame_size = (uint64_t*)w;
 
-    cudaFuncSetAttribute(lz77_blocks_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CompressSmem));
+    constexpr int LZ4_NT = 512;                    // 2 CTAs x 16 warps per SM: throughput scales ~linearly with resident warps
+    cudaFuncSetAttribute(lz77_blocks_kernel<0, LZ4_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CompressSmem));
     const uint32_t maxc = (uint32_t)(zmt_sm_count() * 2 * 8);
     uint32_t gridc = nblocks < maxc ? nblocks : maxc;
+    size_t smem_bytes = sizeof(CompressSmem);
+    if (getenv("ZSTDMT_B200_OCC1")) {          // experiment knob: pad shared memory so that only one CTA fits per SM
+        smem_bytes = 200 * 1024;
+        cudaFuncSetAttribute(lz77_blocks_kernel<0, LZ4_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    }
     { ZmtProfScope ps(ZMT_K_LZ4_COMPRESS, stream);
-    lz77_blocks_kernel<0><<<gridc, C_NT, sizeof(CompressSmem), stream>>>((const uint8_t*)d_in, in_bytes, chunk_size, d_chunk_bytes, bpc, tmp, blk_csize, nblocks, getenv("ZSTDMT_B200_NO_TMA") ? 1u : 0u, nullptr); }
+    lz77_blocks_kernel<0, LZ4_NT><<<gridc, LZ4_NT, smem_bytes, stream>>>((const uint8_t*)d_in, in_bytes, chunk_size, d_chunk_bytes, bpc, tmp, blk_csize, nblocks, getenv("ZSTDMT_B200_NO_TMA") ? 1u : 0u, nullptr); }
     zmt_dbg_check(stream, "lz4_compress_blocks_kernel");
     { ZmtProfScope ps(ZMT_K_XXH32, stream);
     xxh32_kernel<<<(nchunks + X_WARPS - 1) / X_WARPS, 32 * X_WARPS, 0, stream>>>((const uint8_t*)d_in, nullptr, nullptr, d_chunk_bytes, chunk_size, in_bytes, chk, nchunks); }
@@ -1122,10 +1137,10 @@ extern "C" int zmt_zstd_compress_device(const void* d_in, uint64_t in_bytes, uin
     uint64_t* frame_size = (uint64_t*)w; w += ((((uint64_t)nchunks + 1) * 8 + 255) & ~255ull);
     ZScratch* zsc = (ZScratch*)w;
     static_assert(sizeof(ZScratch) % 8 == 0, "scratch stride");
-    cudaFuncSetAttribute(lz77_blocks_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CompressSmem));
+    cudaFuncSetAttribute(lz77_blocks_kernel<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CompressSmem));
     const uint32_t gridc = zstd_grid(nblocks);
     { ZmtProfScope ps(ZMT_K_ZSTD_COMPRESS, stream);
-    lz77_blocks_kernel<1><<<gridc, C_NT, sizeof(CompressSmem), stream>>>((const uint8_t*)d_in, in_bytes, chunk_size, d_chunk_bytes, bpc, tmp, blk_csize, nblocks, getenv("ZSTDMT_B200_NO_TMA") ? 1u : 0u, zsc); }
+    lz77_blocks_kernel<1, 256><<<gridc, 256, sizeof(CompressSmem), stream>>>((const uint8_t*)d_in, in_bytes, chunk_size, d_chunk_bytes, bpc, tmp, blk_csize, nblocks, getenv("ZSTDMT_B200_NO_TMA") ? 1u : 0u, zsc); }
     zmt_dbg_check(stream, "lz77_blocks_kernel<zstd>");
     zstd_frame_sizes_kernel<<<(nchunks + 255) / 256, 256, 0, stream>>>(blk_csize, in_bytes, chunk_size, d_chunk_bytes, bpc, nchunks, frame_size);
     scan_u64_kernel<<<1, 1024, 0, stream>>>(frame_size, d_frame_off, nchunks);
