@@ -146,13 +146,21 @@ def test_decode_golden_fixtures(torch):
 
 
 def test_decode_detects_corruption(torch):
+    """zstd frames of this path carry no checksum (like the reference's), so only structural damage is detectable:
+    a wrong content size, a broken block header, a sequence bitstream that does not end where it must."""
     n = 3 << 20
     src = z.gen_stream(z.GEN_TEXT, n, 1 << 20)
     framed, foff = gpu_compress(torch, src, 1 << 20)
-    bad = framed.copy(); bad[int(foff[1]) + 12 + 9 + 40] ^= 0x5A          # inside frame 1's first block
+    bad = framed.copy(); bad[int(foff[1]) + 12 + 5] ^= 0x01               # frame 1: content size field
     back, status, dec = gpu_decompress(torch, bad)
     assert status[1] != 0 and status[0] == 0 and status[2] == 0
     assert np.array_equal(back[: 1 << 20], src[: 1 << 20])
+    bad = framed.copy(); bad[int(foff[2]) - 1] = 0                          # frame 1: last byte of the last block's bitstream (end marker gone)
+    back, status, dec = gpu_decompress(torch, bad)
+    assert status[1] != 0 and status[0] == 0 and status[2] == 0
+    bad = framed.copy(); bad[int(foff[0]) + 12 + 9] |= 0x06                 # frame 0: first block header -> reserved block type 3
+    dec = z.ZstdDeviceDecompressor(bad)
+    assert not dec.scan_ok                                                  # the host scan already refuses it
 
 
 @pytest.mark.parametrize("n,chunk,level", [(0, 1 << 20, 3), (1, 1 << 20, 3), ((5 << 20) + 77, 1 << 20, 3), ((3 << 20) + 5, 300000, 1), (40 << 20, 4 << 20, 3)])

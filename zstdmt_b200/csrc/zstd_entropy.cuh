@@ -40,6 +40,8 @@ struct ZEnt {
     uint32_t wbase[16];
     uint32_t nused, maxsym, maxcnt, maxbits, mode;
     uint32_t seqbits, fin[3];        // final FSE states
+    uint8_t  wdesc[136];             // Huffman tree description when coded with FSE (header byte + <= 127 bytes)
+    uint32_t wdesc_len;
 };
 
 // ---- predefined-distribution FSE encoding tables (filled by the host once per device: zstd_tables_init)
@@ -92,6 +94,97 @@ __device__ __forceinline__ void z_load_fse_shared(ZFseShared& F, uint32_t tid, u
         const ZFseCTable& T = k == 0 ? c_fse_ll : k == 1 ? c_fse_of : c_fse_ml;
         F.state[k][j] = T.state[j]; F.tt[k][j] = make_int2(T.dnb[j], T.dfs[j]);
     }
+}
+
+// FSE-compress the Huffman weights (RFC 8878 §4.2.1.2; HUF_compressWeights + FSE_writeNCount + FSE_compress_usingCTable
+// [ext]) — one thread, at most 255 weights over an alphabet of <= 12 values, table log 6.  Writes header byte (= size)
+// + payload into Z.wdesc, returns the total length or 0 when the weights are not compressible this way.
+__device__ uint32_t z_fse_weights(ZEnt& Z, uint32_t nw /* weights listed = maxsym */, uint32_t maxbits)
+{
+    uint8_t* wt = reinterpret_cast<uint8_t*>(Z.ncnt);              // scratch: weights (256 B) | state table | symbol tt
+    uint16_t* stab = reinterpret_cast<uint16_t*>(Z.ncnt + 64);     // 64 entries
+    int32_t* dnb = reinterpret_cast<int32_t*>(Z.ncnt + 96);        // 16
+    int32_t* dfs = reinterpret_cast<int32_t*>(Z.ncnt + 112);       // 16
+    if (nw < 2) return 0;
+    uint32_t count[13]; int norm[13];
+    for (int i = 0; i < 13; i++) count[i] = 0;
+    uint32_t maxw = 0;
+    for (uint32_t s = 0; s < nw; s++) { const uint32_t w = Z.hlen[s] ? maxbits + 1 - Z.hlen[s] : 0; wt[s] = (uint8_t)w; count[w]++; if (w > maxw) maxw = w; }
+    uint32_t maxc = 0; for (uint32_t i = 0; i <= maxw; i++) maxc = count[i] > maxc ? count[i] : maxc;
+    if (maxc == nw || maxc <= 1) return 0;                          // one symbol only / nothing repeats
+    // ---- normalise to 64 (every present value >= 1)
+    const int LOG = 6, SIZE = 64;
+    int sum = 0, big = 0;
+    for (uint32_t i = 0; i <= maxw; i++) { norm[i] = count[i] ? (int)((count[i] * (uint32_t)SIZE) / nw) : 0; if (count[i] && norm[i] == 0) norm[i] = 1; sum += norm[i]; if (count[i] > count[big]) big = (int)i; }
+    while (sum != SIZE) {
+        if (sum < SIZE) { norm[big] += SIZE - sum; sum = SIZE; }
+        else {                                                       // take from the largest entries, never below 1
+            int b2 = -1; for (uint32_t i = 0; i <= maxw; i++) if (norm[i] > 1 && (b2 < 0 || norm[i] > norm[b2])) b2 = (int)i;
+            if (b2 < 0) return 0;
+            const int take = (norm[b2] - 1) < (sum - SIZE) ? (norm[b2] - 1) : (sum - SIZE);
+            norm[b2] -= take; sum -= take;
+        }
+    }
+    // ---- NCount header (forward bit order)
+    uint8_t* out = Z.wdesc + 1; uint32_t bitpos = 0;
+    for (int i = 0; i < 135; i++) Z.wdesc[i] = 0;
+    auto put = [&](uint32_t v, uint32_t nb) { for (uint32_t k = 0; k < nb; k++, bitpos++) if ((v >> k) & 1) out[bitpos >> 3] |= (uint8_t)(1u << (bitpos & 7)); };
+    put((uint32_t)(LOG - 5), 4);
+    {
+        int remaining = SIZE + 1, threshold = SIZE, nbBits = LOG + 1; uint32_t sym = 0; bool prev0 = false;
+        const uint32_t alpha = maxw + 1;
+        while (sym < alpha && remaining > 1) {
+            if (prev0) {
+                uint32_t start = sym;
+                while (sym < alpha && norm[sym] == 0) sym++;
+                if (sym == alpha) break;
+                while (sym >= start + 3) { start += 3; put(3, 2); }
+                put(sym - start, 2);
+            }
+            int cnt = norm[sym++];
+            const int mx = (2 * threshold - 1) - remaining;
+            remaining -= cnt;
+            cnt++;
+            if (cnt >= threshold) cnt += mx;
+            put((uint32_t)cnt, (uint32_t)nbBits - ((cnt < mx) ? 1u : 0u));
+            prev0 = (cnt == 1);
+            while (remaining < threshold) { nbBits--; threshold >>= 1; }
+        }
+        if (remaining != 1) return 0;
+    }
+    const uint32_t hdr_bytes = (bitpos + 7) >> 3;
+    // ---- encoding table (FSE_buildCTable)
+    {
+        int cumul[14]; uint8_t tsym[64]; int pos = 0; const int step = (SIZE >> 1) + (SIZE >> 3) + 3;
+        cumul[0] = 0; for (uint32_t u = 1; u <= maxw + 1; u++) cumul[u] = cumul[u - 1] + norm[u - 1];
+        for (uint32_t sy = 0; sy <= maxw; sy++) for (int i = 0; i < norm[sy]; i++) { tsym[pos] = (uint8_t)sy; pos = (pos + step) & (SIZE - 1); }
+        for (int u = 0; u < SIZE; u++) { const int sy = tsym[u]; stab[cumul[sy]++] = (uint16_t)(SIZE + u); }
+        int total = 0;
+        for (uint32_t sy = 0; sy <= maxw; sy++) {
+            const int n = norm[sy];
+            if (n == 0) { dnb[sy] = ((LOG + 1) << 16) - SIZE; dfs[sy] = 0; }
+            else if (n == 1) { dnb[sy] = (LOG << 16) - SIZE; dfs[sy] = total - 1; total++; }
+            else { const int hb = 31 - __clz((uint32_t)(n - 1)); const int mbo = LOG - hb; dnb[sy] = (mbo << 16) - (n << mbo); dfs[sy] = total - n; total += n; }
+        }
+    }
+    // ---- two interleaved states, last weight first (FSE_compress_usingCTable_generic)
+    uint8_t* bs = out + hdr_bytes; uint32_t bpos = 0;
+    const uint32_t bcap = (127 - hdr_bytes) * 8;                     // the FSE form must fit 127 bytes (header byte < 128)
+    bool over = false;
+    auto putb = [&](uint32_t v, uint32_t nb) { for (uint32_t k = 0; k < nb; k++, bpos++) { if (bpos >= bcap) { over = true; return; } if ((v >> k) & 1) bs[bpos >> 3] |= (uint8_t)(1u << (bpos & 7)); } };
+    auto init = [&](uint32_t sy) -> uint32_t { const uint32_t nbo = (uint32_t)(dnb[sy] + (1 << 15)) >> 16; return stab[(((nbo << 16) - (uint32_t)dnb[sy]) >> nbo) + dfs[sy]]; };
+    auto enc = [&](uint32_t& st, uint32_t sy) { const uint32_t nbo = (st + (uint32_t)dnb[sy]) >> 16; putb(st & ((1u << nbo) - 1), nbo); st = stab[(st >> nbo) + dfs[sy]]; };
+    if (hdr_bytes >= 100) return 0;
+    int ip = (int)nw; uint32_t s1, s2;
+    if (nw & 1) { s1 = init(wt[--ip]); s2 = init(wt[--ip]); enc(s1, wt[--ip]); }
+    else { s2 = init(wt[--ip]); s1 = init(wt[--ip]); }
+    while (ip > 0) { enc(s2, wt[--ip]); enc(s1, wt[--ip]); }
+    putb(s2, (uint32_t)LOG); putb(s1, (uint32_t)LOG);
+    putb(1, 1);
+    const uint32_t total_bytes = hdr_bytes + ((bpos + 7) >> 3);
+    if (over || total_bytes >= 128) return 0;
+    Z.wdesc[0] = (uint8_t)total_bytes;
+    return 1 + total_bytes;
 }
 
 // named barrier for the 7 literal warps (224 threads); barrier 0 stays the CTA-wide one
@@ -185,7 +278,7 @@ __device__ uint32_t z_encode_block(ZEnt& Z, const ZFseShared& F, ZScratch* zs, u
         const uint32_t nused = Z.nused, maxsym = Z.maxsym;
         uint32_t lmode = 0;                                  // 0 raw, 1 RLE, 2 Huffman (direct-weight trees only: symbols 0..128)
         if (nlit && Z.maxcnt == nlit) lmode = 1;
-        else if (nlit >= 64 && maxsym <= 128 && nused >= 2) lmode = 2;
+        else if (nlit >= 64 && nused >= 2) lmode = 2;
         uint32_t tree_bytes = 0, lit_payload = 0, sbytes[4] = {0, 0, 0, 0}, swords[4] = {0, 0, 0, 0};
         if (lmode == 2) {
             // order[]: present symbols by ascending (count, symbol)
@@ -254,9 +347,17 @@ __device__ uint32_t z_encode_block(ZEnt& Z, const ZFseShared& F, ZScratch* zs, u
             }
             uint32_t totbits;
             (void)z_lit_exscan(mybitsum, scanws, &totbits);
-            tree_bytes = 1 + (maxsym + 1) / 2;
+            // tree description: FSE-coded weights when smaller (or when direct 4-bit weights cannot express symbols > 128)
+            if (tid == 0) {
+                const uint32_t direct = maxsym <= 128 ? 1 + (maxsym + 1) / 2 : 0xFFFFu;
+                const uint32_t fl = z_fse_weights(Z, maxsym, maxbits);
+                Z.wdesc_len = (fl && fl < direct) ? fl : (direct != 0xFFFFu ? 0u : 0xFFFFu);       // 0: direct form, 0xFFFF: no valid form
+            }
+            z_lit_sync();
+            const uint32_t wl = Z.wdesc_len;
+            tree_bytes = wl == 0 ? 1 + (maxsym + 1) / 2 : wl;
             const uint32_t est = (totbits + 7) / 8 + 4 + tree_bytes + 6;
-            if (est >= nlit || est + 64 > Z_BITWORDS * 4) lmode = 0;       // Huffman does not pay (or would not fit the bit buffer)
+            if (wl == 0xFFFFu || est >= nlit || est + 64 > Z_BITWORDS * 4) lmode = 0;       // Huffman does not pay (or would not fit the bit buffer)
         }
         uint32_t lit_hdr, lit_body;
         if (lmode == 2) {
@@ -295,11 +396,14 @@ __device__ uint32_t z_encode_block(ZEnt& Z, const ZFseShared& F, ZScratch* zs, u
                 const uint64_t v = 2ull | ((uint64_t)fmt << 2) | ((uint64_t)nlit << 4) | ((uint64_t)lit_body << (4 + nb));
                 for (uint32_t i = 0; i < lit_hdr; i++) p[i] = (uint8_t)(v >> (8 * i));
                 uint8_t* q = p + lit_hdr;
-                *q++ = (uint8_t)(127 + maxsym);             // direct weights for symbols 0 .. maxsym-1 (the last one is implied)
-                for (uint32_t s = 0; s < maxsym; s += 2) {
-                    const uint32_t w0 = Z.hlen[s] ? Z.maxbits + 1 - Z.hlen[s] : 0;
-                    const uint32_t w1 = (s + 1 < maxsym && Z.hlen[s + 1]) ? Z.maxbits + 1 - Z.hlen[s + 1] : 0;
-                    *q++ = (uint8_t)((w0 << 4) | w1);
+                if (Z.wdesc_len) { for (uint32_t i = 0; i < Z.wdesc_len; i++) *q++ = Z.wdesc[i]; }       // FSE-coded weights
+                else {
+                    *q++ = (uint8_t)(127 + maxsym);         // direct weights for symbols 0 .. maxsym-1 (the last one is implied)
+                    for (uint32_t s = 0; s < maxsym; s += 2) {
+                        const uint32_t w0 = Z.hlen[s] ? Z.maxbits + 1 - Z.hlen[s] : 0;
+                        const uint32_t w1 = (s + 1 < maxsym && Z.hlen[s + 1]) ? Z.maxbits + 1 - Z.hlen[s + 1] : 0;
+                        *q++ = (uint8_t)((w0 << 4) | w1);
+                    }
                 }
                 q[0] = (uint8_t)sbytes[0]; q[1] = (uint8_t)(sbytes[0] >> 8); q[2] = (uint8_t)sbytes[1]; q[3] = (uint8_t)(sbytes[1] >> 8);
                 q[4] = (uint8_t)sbytes[2]; q[5] = (uint8_t)(sbytes[2] >> 8);
