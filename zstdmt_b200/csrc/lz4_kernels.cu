@@ -1,4 +1,6 @@
-// lz4_kernels.cu — hand-written sm_100a kernels for the LZ4 side of the zstdmt hot path.
+// lz4_kernels.cu — hand-written sm_100a kernels: the LZ77 front end shared by both codecs, the LZ4 back end
+// (block format, XXH32, frame pack, decoder) and the launchers of the Zstandard encoder (entropy stage in
+// zstd_entropy.cuh; the Zstandard decoder lives in zstd_decode.cu).
 //
 // Replaces the arithmetic the reference reaches through
 //   LZ4F_compressFrame   (/root/reference/lib/lz4-mt_compress.c:280-283)
@@ -6,7 +8,7 @@
 // plus the 12-byte skippable container write (lib/lz4-mt_compress.c:293-298).
 //
 // Kernels
-//   lz4_compress_blocks_kernel  one CTA per 64 KiB LZ4F block; block staged in SMEM by the TMA
+//   lz77_blocks_kernel<codec,NT> one CTA per 64 KiB block (LZ4F block / zstd match window); block staged in SMEM by the TMA
 //                               unit (cp.async.bulk); round-synchronous hash candidates,
 //                               speculative-chain parallel greedy parse, scan-based emission.
 //   xxh32_kernel                4 lanes per chunk (the 4 XXH32 accumulators), 8 chunks per warp.
@@ -70,7 +72,6 @@ struct __align__(16) CompressSmem {
     uint32_t min_[C_NT];                  // entry (free) position of a reachable chain
     uint16_t link[C_NT];                  // chain this chain merges into (C_END: leaves the tile)
     uint16_t jump[C_NT];
-    uint8_t  reach[C_NT];
     uint16_t entry[8];                    // per warp: first chain of the true path inside it (0xFFFF: none)
     uint16_t piece[C_MAXPIECE];           // tile-relative start of the r-th selected piece
     uint16_t hidx[C_MAXPIECE];            // piece index of the h-th head
