@@ -106,8 +106,8 @@ __device__ __forceinline__ uint32_t c_extend(const uint8_t* s, uint32_t p, uint3
 //   MODE 0: own segment only (sets V, caches len, exit state -> xfree/xdin)
 //   MODE 1: continuation until it merges into another chain or leaves the tile (-> link/mpos)
 //   MODE 2: re-walk of a chain that is on the true path: marks Sel/Cont (same steps as MODE 0 + 1)
-template <int MODE>
-__device__ __forceinline__ void c_walk(CompressSmem& S, uint32_t k, uint32_t p, uint32_t din, uint32_t t0, uint32_t limit)
+template <int MODE, class SM>
+__device__ __forceinline__ void c_walk(SM& S, uint32_t k, uint32_t p, uint32_t din, uint32_t t0, uint32_t limit)
 {
     const uint32_t t1 = t0 + C_TILE;
     uint32_t lk = 0xFFFFFFFFu, mp = 0;
@@ -169,7 +169,8 @@ __device__ __forceinline__ uint32_t c_seq_size(uint32_t lit, uint32_t L)
 
 // writes one LZ4 sequence at op (token, lengths, offset); literals longer than C_LONGLIT are queued for a
 // warp-cooperative copy.  Returns the encoded size.
-__device__ __forceinline__ uint32_t c_emit_seq(CompressSmem& S, uint8_t* dst, uint32_t o, uint32_t lit_start, uint32_t lit, uint32_t off, uint32_t mlen)
+template <class SM>
+__device__ __forceinline__ uint32_t c_emit_seq(SM& S, uint8_t* dst, uint32_t o, uint32_t lit_start, uint32_t lit, uint32_t off, uint32_t mlen)
 {
     uint8_t* op = dst + o;
     const uint32_t ml = mlen - 4;
@@ -504,6 +505,8 @@ lz77_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32_t c
         }
     }
 }
+
+#include "lz4_pipe.cuh"
 
 // ============================================================================ XXH32 (content checksum)
 // One warp per buffer.  XXH32 is four serial accumulator chains (one per 32-bit word of every 16-byte
@@ -1080,9 +1083,21 @@ extern "C" int zmt_lz4_compress_device(const void* d_in, uint64_t in_bytes, uint
         smem_bytes = 200 * 1024;
         cudaFuncSetAttribute(lz77_blocks_kernel<0, LZ4_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     }
+    static const bool no_pipe = getenv("ZSTDMT_B200_NOPIPE") != nullptr;   // A/B knob: single-team schedule (same output bytes)
     { ZmtProfScope ps(ZMT_K_LZ4_COMPRESS, stream);
-    lz77_blocks_kernel<0, LZ4_NT><<<gridc, LZ4_NT, smem_bytes, stream>>>((const uint8_t*)d_in, in_bytes, chunk_size, d_chunk_bytes, bpc, tmp, blk_csize, nblocks, getenv("ZSTDMT_B200_NO_TMA") ? 1u : 0u, nullptr); }
-    zmt_dbg_check(stream, "lz4_compress_blocks_kernel");
+    if (no_pipe || smem_bytes != sizeof(CompressSmem))
+        lz77_blocks_kernel<0, LZ4_NT><<<gridc, LZ4_NT, smem_bytes, stream>>>((const uint8_t*)d_in, in_bytes, chunk_size, d_chunk_bytes, bpc, tmp, blk_csize, nblocks, getenv("ZSTDMT_B200_NO_TMA") ? 1u : 0u, nullptr);
+    else {
+        cudaFuncSetAttribute(lz4_blocks_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PipeSmem));
+        static bool occ_shown = false;
+        if (!occ_shown && getenv("ZSTDMT_B200_SHOW_OCC")) {
+            int nb = 0; occ_shown = true;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, lz4_blocks_pipe_kernel, 2 * P_TEAM, sizeof(PipeSmem));
+            fprintf(stderr, "[zstdmt_b200] lz4_blocks_pipe_kernel: %d CTAs/SM, %zu B smem\n", nb, sizeof(PipeSmem));
+        }
+        lz4_blocks_pipe_kernel<<<gridc, 2 * P_TEAM, sizeof(PipeSmem), stream>>>((const uint8_t*)d_in, in_bytes, chunk_size, d_chunk_bytes, bpc, tmp, blk_csize, nblocks, getenv("ZSTDMT_B200_NO_TMA") ? 1u : 0u);
+    } }
+    zmt_dbg_check(stream, "lz4 block compressor");
     { ZmtProfScope ps(ZMT_K_XXH32, stream);
     xxh32_kernel<<<(nchunks + X_WARPS - 1) / X_WARPS, 32 * X_WARPS, 0, stream>>>((const uint8_t*)d_in, nullptr, nullptr, d_chunk_bytes, chunk_size, in_bytes, chk, nchunks); }
     zmt_dbg_check(stream, "xxh32_kernel");
