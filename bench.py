@@ -9,7 +9,7 @@ A step = one pass of the per-chunk compress hot path over the whole 8 GiB batch 
   value : GB/s of (raw bytes in + framed bytes out), device-timed with CUDA events, inputs resident in HBM
   e2e   : same metric through the reference-shaped callback API (LZ4MT_compressCCtx, host buffers; the
           pinned staging copies and H2D/D2H are inside the timed region)
-  roofline : the dominant kernel (lz77_blocks_kernel<0,512>, the LZ4 block compressor) against the measured HBM copy peak
+  roofline : the dominant kernel (lz4_blocks_pipe_kernel, the LZ4 block compressor) against the measured HBM copy peak
   cpu_baseline : the unmodified reference (oracle/_ref: lib/lz4-mt_*.c + liblz4 1.9.4) on this box's cores
 Multi-GPU: chunks are dealt round-robin (chunk i -> rank i mod N), no collective on the data path;
 weak scaling (8 GiB per GPU); time = max over ranks.
@@ -403,7 +403,7 @@ def run_b200(args):
                 "api": "LZ4MT_compressCCtx via in-memory fn_read/fn_write (csrc/memio_glue.c), threads=%d" % threads, "ms_per_step": e2e_s / args.steps * 1e3},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic_per_launch(algo_bytes_compress(n, framed)),
-                     "kernel": "lz77_blocks_kernel<0,512> (LZ4 instantiation)", "kernel_ms": kernel_ms, "peak_source": peak_src,
+                     "kernel": "lz4_blocks_pipe_kernel (LZ4 block compressor, two-team pipeline)", "kernel_ms": kernel_ms, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo_bytes_compress(n, framed)},
         "extra": extra,
     }

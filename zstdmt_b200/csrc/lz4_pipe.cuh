@@ -85,13 +85,19 @@ struct PipeView {
 // may touch: while only HALF-slots are being updated the other half of each word is constant, so
 // atomicMax(word, other_half | val << shift) leaves it alone and maximises ours.  The caller runs the two
 // passes with a team barrier in between.
+// Written as predicated PTX: a branch per (position, pass) costs more instructions than the update itself.
 template <uint32_t HALF>
-__device__ __forceinline__ void tab16_max(uint16_t* tab, uint32_t h, uint32_t val)
+__device__ __forceinline__ void tab16_max(uint32_t tab_s32, uint32_t h, uint32_t val)
 {
-    uint32_t* w = reinterpret_cast<uint32_t*>(tab) + (h >> 1);
-    const uint32_t cur = *reinterpret_cast<volatile uint32_t*>(w);
-    if (HALF) atomicMax(w, (val << 16) | (cur & 0xFFFFu));
-    else      atomicMax(w, (cur & 0xFFFF0000u) | val);
+    const uint32_t addr = tab_s32 + ((h >> 1) << 2);
+    // invalid positions carry h = 0xFFFFFFFF: bit 31 set -> never selected
+    const uint32_t sel = HALF ? ((h & 0x80000001u) == 1u) : ((h & 0x80000001u) == 0u);
+    if (HALF)
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 c;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.volatile.shared.u32 c, [%0];\n\t@p and.b32 c, c, 0xFFFF;\n\t@p or.b32 c, c, %1;\n\t@p red.shared.max.u32 [%0], c;\n\t}"
+                     ::"r"(addr), "r"(val << 16), "r"(sel) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 c;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.volatile.shared.u32 c, [%0];\n\t@p and.b32 c, c, 0xFFFF0000;\n\t@p or.b32 c, c, %1;\n\t@p red.shared.max.u32 [%0], c;\n\t}"
+                     ::"r"(addr), "r"(val), "r"(sel) : "memory");
 }
 
 // exclusive scan over one team (8 warps); one team barrier; `ws` = two 16-word halves used alternately
@@ -153,6 +159,7 @@ lz4_blocks_pipe_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32
         if (team == 0) {
             // =========================================================== front end: candidates, chains, true path
             uint32_t e = 0, e_din = 0;                    // team-uniform parse state (position, offset of the open match)
+            const uint32_t tab_s32 = smem_u32(S.tab);
             for (uint32_t ti = 0; ti < ntiles; ti++) {
                 const uint32_t t0 = ti * C_TILE, t1 = t0 + C_TILE, b = ti & 1;
                 PipeTile& T = S.tile[b];
@@ -193,11 +200,11 @@ lz4_blocks_pipe_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32
                     if (r == 0 && ttid == 0) S.a_any[b ^ 1] = 0;       // every reader of the previous tile's flag is past it
 #pragma unroll
                     for (uint32_t k = 0; k < KPR; k++)
-                        if (hreg[k] != 0xFFFFFFFFu && (hreg[k] & 1u)) tab16_max<1>(S.tab, hreg[k], t0 + r * C_ROUND + k * P_TEAM + ttid + 1);
+                        tab16_max<1>(tab_s32, hreg[k], t0 + r * C_ROUND + k * P_TEAM + ttid + 1);
                     TEAM_A_SYNC();
 #pragma unroll
                     for (uint32_t k = 0; k < KPR; k++)
-                        if (hreg[k] != 0xFFFFFFFFu && !(hreg[k] & 1u)) tab16_max<0>(S.tab, hreg[k], t0 + r * C_ROUND + k * P_TEAM + ttid + 1);
+                        tab16_max<0>(tab_s32, hreg[k], t0 + r * C_ROUND + k * P_TEAM + ttid + 1);
                     TEAM_A_SYNC();
                 }
                 if (lane == 0 && anyM) atomicOr(&S.a_any[b], 1u);
