@@ -56,6 +56,7 @@ __device__ __forceinline__ uint64_t zmt_chunk_len(const uint32_t* __restrict__ c
 #define C_END        0xFFFFu       // link: chain leaves the tile
 
 struct __align__(16) CompressSmem {
+    static constexpr bool relen = false;   // chain walks cache piece lengths in len[] for the marking walk
     uint8_t  pad0[16];                    // bytes "before" the block (read by the 8-byte window of phase 1, never matched)
     uint8_t  in[LZ4_BLK + 32];            // block bytes + zero pad
     uint32_t tab[1 << C_HASHLOG];         // hash -> 1 + position
@@ -87,17 +88,18 @@ struct __align__(16) CompressSmem {
 
 static_assert(offsetof(CompressSmem, fse) - offsetof(CompressSmem, off) >= sizeof(ZEnt), "entropy scratch must fit in the tile arrays");
 
-// number of bytes (<= cap) for which s[p + i] == s[p + i - d]
+// number of bytes (<= cap) for which s[p + i] == s[p + i - d].  Word compares only: the last, partial word gets a
+// sentinel bit at byte `cap` (reads run at most 3 bytes past p + cap: S.in carries 32 pad bytes).
 __device__ __forceinline__ uint32_t c_extend(const uint8_t* s, uint32_t p, uint32_t d, uint32_t cap)
 {
     uint32_t L = 0;
-    while (L + 4 <= cap) {
-        const uint32_t x = lds32u(s, p + L) ^ lds32u(s, p + L - d);
+    for (;;) {
+        uint32_t x = lds32u(s, p + L) ^ lds32u(s, p + L - d);
+        const uint32_t rem = cap - L;
+        if (rem < 4) x |= 1u << (8 * rem);
         if (x) return L + ((__ffs(x) - 1) >> 3);
         L += 4;
     }
-    while (L < cap && s[p + L] == s[p + L - d]) L++;
-    return L;
 }
 
 // Walk one speculative chain through the tile.  The greedy parse is evaluated piecewise: a match is cut at
@@ -145,12 +147,15 @@ __device__ __forceinline__ void c_walk(SM& S, uint32_t k, uint32_t p, uint32_t d
         uint32_t B = (q & ~(C_SEG - 1)) + C_SEG;                     // cut at the first boundary leaving >= 4 bytes
         if (B - q < 4) B += C_SEG;
         uint32_t L;
-        if (MODE == 2) { atomicOr(&S.Sel[qr >> 5], 1u << (qr & 31)); L = S.len[qr]; }
+        if (MODE == 2 && !SM::relen) { atomicOr(&S.Sel[qr >> 5], 1u << (qr & 31)); L = S.len[qr]; }
         else {
             const uint32_t end = B < limit ? B : limit;
             L = 4 + c_extend(S.in, q + 4, d, end - (q + 4));        // first 4 bytes are known equal; q + 4 <= limit always
-            S.len[qr] = (uint8_t)L;
-            if (MODE == 0) atomicOr(&S.V[qr >> 5], 1u << (qr & 31));
+            if (MODE == 2) { atomicOr(&S.Sel[qr >> 5], 1u << (qr & 31)); S.len[qr] = (uint8_t)L; }   // relen: len[] belongs to the marking team
+            else {
+                if (!SM::relen) S.len[qr] = (uint8_t)L;
+                if (MODE == 0) atomicOr(&S.V[qr >> 5], 1u << (qr & 31));
+            }
         }
         p = q + L;
         if (p == B) din = d;                                          // reached the boundary: still inside the match
@@ -177,7 +182,11 @@ __device__ __forceinline__ uint32_t c_emit_seq(SM& S, uint8_t* dst, uint32_t o, 
     *op++ = (uint8_t)(((lit >= 15 ? 15u : lit) << 4) | (ml >= 15 ? 15u : ml));
     if (lit >= 15) { uint32_t x = lit - 15; while (x >= 255) { *op++ = 255; x -= 255; } *op++ = (uint8_t)x; }
     if (lit <= C_LONGLIT) { for (uint32_t i = 0; i < lit; i++) op[i] = S.in[lit_start + i]; }
-    else { const uint32_t s = atomicAdd(&S.nlong, 1u); S.longl[3 * s] = lit_start; S.longl[3 * s + 1] = (uint32_t)(op - dst); S.longl[3 * s + 2] = lit; }
+    else {
+        const uint32_t s = atomicAdd(&S.nlong, 1u);
+        if (SM::relen) { S.longl[2 * s] = lit_start | (lit << 16); S.longl[2 * s + 1] = (uint32_t)(op - dst); }     // pipelined kernel: packed (both < 65536)
+        else { S.longl[3 * s] = lit_start; S.longl[3 * s + 1] = (uint32_t)(op - dst); S.longl[3 * s + 2] = lit; }
+    }
     op += lit;
     *op++ = (uint8_t)off; *op++ = (uint8_t)(off >> 8);
     if (ml >= 15) { uint32_t x = ml - 15; while (x >= 255) { *op++ = 255; x -= 255; } *op++ = (uint8_t)x; }

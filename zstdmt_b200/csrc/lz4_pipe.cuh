@@ -9,9 +9,10 @@
 // FULL[b] producer -> consumer, EMPTY[b] consumer -> producer.  With 2 CTAs per SM this gives four independent
 // instruction streams per SM instead of two (the kernel is issue/latency bound: DESIGN.md §3).
 //
-// Shared memory: the double-buffered tile arrays cost 13.5 KB; the hash table pays for them by holding
-// 16-bit positions (block positions < 65536), max-updated with the native 32-bit atomicMax in two passes
-// (odd slots, then even slots: see tab16_max).
+// Shared memory: only what crosses the teams is double-buffered (off, M, V, entry positions, path mask: 9.5 KB per
+// buffer).  Piece lengths do not cross: the front end does not store them, the marking walk of the back end
+// recomputes them for the true-path pieces only (it has the slack), which keeps the 32-bit hash table and its
+// single-pass atomicMax.  (A 16-bit table was tried first: CAS loop 15 %, two-pass atomicMax 8 % of all instructions.)
 #pragma once
 
 #define P_TEAM      256u
@@ -19,6 +20,7 @@
 #define PB_B        2u
 #define PB_FULL0    3u
 #define PB_EMPTY0   5u
+#define P_MAXPIECE  1280u         // 4096/4 match pieces + 256 continuation pieces, multiple of 256
 
 // Barrier ids are immediates: ptxas reserves only the ids it sees (a register id makes it reserve all 16,
 // and barriers are an occupancy resource).
@@ -40,10 +42,9 @@ __device__ __forceinline__ void bar_arrive()
 
 struct __align__(16) PipeTile {
     uint16_t off[C_TILE];                 // candidate offset per tile position (0 = none)
-    uint8_t  len[C_TILE];                 // piece length per piece start
     uint32_t M[C_TILE / 32];              // has-candidate bits
     uint32_t V[C_TILE / 32];              // visited-by-own-chain bits
-    uint16_t min_[C_CHAINS];              // tile-relative entry position of a chain on the true path
+    uint8_t  min_[C_CHAINS];              // entry position of a chain on the true path, relative to its own segment (< 16)
     uint32_t pathmask[C_CHAINS / 32];     // chains on the true path
     uint32_t k0, e_din, do_parse, pad;    // entry chain, offset of the match open at the entry, tile has work
 };
@@ -51,24 +52,25 @@ struct __align__(16) PipeTile {
 struct __align__(16) PipeSmem {
     uint8_t  pad0[16];
     uint8_t  in[LZ4_BLK + 32];
-    uint16_t tab[1 << C_HASHLOG];         // hash -> 1 + position (positions with 12 bytes left: < 65525)
+    uint32_t tab[1 << C_HASHLOG];         // hash -> 1 + position
     PipeTile tile[2];
     // ---- front end (team A)
     uint32_t xfree[C_CHAINS];
     uint32_t mpos[C_CHAINS];
     uint16_t xdin[C_CHAINS];
     uint16_t link[C_CHAINS];
-    uint16_t jump[C_CHAINS];
+    uint8_t  jump[C_CHAINS];
     uint16_t entry[8];
     uint32_t e_next, d_next;
     uint32_t a_any[2];
     // ---- back end (team B)
     uint32_t Sel[C_TILE / 32];
     uint32_t Cont[C_TILE / 32];
-    uint16_t piece[C_MAXPIECE];
-    uint16_t hidx[C_MAXPIECE];
-    uint32_t longl[3 * (C_TILE / C_LONGLIT + 2)];
-    __align__(16) uint32_t scanws[32];
+    uint8_t  len[C_TILE];                 // piece length per selected piece start (written by the marking walk)
+    uint16_t piece[P_MAXPIECE];
+    uint16_t hidx[C_TILE / 4];            // heads: one per sequence, sequences hold a match of >= 4 bytes
+    uint32_t longl[2 * (C_TILE / (C_LONGLIT + 1) + 2)];   // (start | length << 16, output offset) of literal runs > C_LONGLIT
+    __align__(16) uint32_t scanws[16];
     uint32_t nlong;
     uint32_t fin_anchor, fin_out;
     uint64_t mbar;
@@ -77,37 +79,19 @@ static_assert(sizeof(PipeSmem) + 1024 <= (228 * 1024) / 2, "two CTAs per SM");
 
 // what c_walk / c_emit_seq touch, with the tile arrays of the current buffer
 struct PipeView {
+    static constexpr bool relen = true;   // the front end does not keep piece lengths: the marking walk recomputes them
     const uint8_t* in; uint16_t* off; uint8_t* len; uint32_t* M; uint32_t* V; uint32_t* Sel; uint32_t* Cont;
     uint32_t* xfree; uint16_t* xdin; uint16_t* link; uint32_t* mpos; uint32_t* longl; uint32_t& nlong;
 };
 
-// Max-update of one 16-bit slot with a native 32-bit atomicMax.  HALF selects which half of every word this pass
-// may touch: while only HALF-slots are being updated the other half of each word is constant, so
-// atomicMax(word, other_half | val << shift) leaves it alone and maximises ours.  The caller runs the two
-// passes with a team barrier in between.
-// Written as predicated PTX: a branch per (position, pass) costs more instructions than the update itself.
-template <uint32_t HALF>
-__device__ __forceinline__ void tab16_max(uint32_t tab_s32, uint32_t h, uint32_t val)
-{
-    const uint32_t addr = tab_s32 + ((h >> 1) << 2);
-    // invalid positions carry h = 0xFFFFFFFF: bit 31 set -> never selected
-    const uint32_t sel = HALF ? ((h & 0x80000001u) == 1u) : ((h & 0x80000001u) == 0u);
-    if (HALF)
-        asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 c;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.volatile.shared.u32 c, [%0];\n\t@p and.b32 c, c, 0xFFFF;\n\t@p or.b32 c, c, %1;\n\t@p red.shared.max.u32 [%0], c;\n\t}"
-                     ::"r"(addr), "r"(val << 16), "r"(sel) : "memory");
-    else
-        asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 c;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.volatile.shared.u32 c, [%0];\n\t@p and.b32 c, c, 0xFFFF0000;\n\t@p or.b32 c, c, %1;\n\t@p red.shared.max.u32 [%0], c;\n\t}"
-                     ::"r"(addr), "r"(val), "r"(sel) : "memory");
-}
-
-// exclusive scan over one team (8 warps); one team barrier; `ws` = two 16-word halves used alternately
+// exclusive scan over one team (8 warps); one team barrier; `ws` = two 8-word halves used alternately
 template <uint32_t BARID>
 __device__ __forceinline__ uint32_t team_exscan1(uint32_t v, uint32_t* ws, uint32_t parity, uint32_t* total, uint32_t twid, uint32_t lane)
 {
     uint32_t inc = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(ZMT_FULL_MASK, inc, d); if (lane >= (uint32_t)d) inc += y; }
-    uint32_t* w = ws + 16 * (parity & 1);
+    uint32_t* w = ws + 8 * (parity & 1);
     if (lane == 31) w[twid] = inc;
     bar_sync<BARID, P_TEAM>();
     const uint4 a = *reinterpret_cast<const uint4*>(w), b = *reinterpret_cast<const uint4*>(w + 4);
@@ -149,7 +133,7 @@ lz4_blocks_pipe_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32
         for (uint32_t i = nb16 + tid; i < n; i += NT) S.in[i] = src[i];
         for (uint32_t i = n + tid; i < ((n + 3) & ~3u) + 32 && i < LZ4_BLK + 32; i += NT) S.in[i] = 0;
         if (tid < 16) S.pad0[tid] = 0;
-        for (uint32_t i = tid; i < (1u << C_HASHLOG) / 2; i += NT) reinterpret_cast<uint32_t*>(S.tab)[i] = 0;
+        for (uint32_t i = tid; i < (1u << C_HASHLOG); i += NT) S.tab[i] = 0;
         if (tid == 0 && nb16) { mbar_wait(&S.mbar, 0); asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&S.mbar))); }
         CTA_SYNC();
 
@@ -159,7 +143,6 @@ lz4_blocks_pipe_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32
         if (team == 0) {
             // =========================================================== front end: candidates, chains, true path
             uint32_t e = 0, e_din = 0;                    // team-uniform parse state (position, offset of the open match)
-            const uint32_t tab_s32 = smem_u32(S.tab);
             for (uint32_t ti = 0; ti < ntiles; ti++) {
                 const uint32_t t0 = ti * C_TILE, t1 = t0 + C_TILE, b = ti & 1;
                 PipeTile& T = S.tile[b];
@@ -200,11 +183,7 @@ lz4_blocks_pipe_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32
                     if (r == 0 && ttid == 0) S.a_any[b ^ 1] = 0;       // every reader of the previous tile's flag is past it
 #pragma unroll
                     for (uint32_t k = 0; k < KPR; k++)
-                        tab16_max<1>(tab_s32, hreg[k], t0 + r * C_ROUND + k * P_TEAM + ttid + 1);
-                    TEAM_A_SYNC();
-#pragma unroll
-                    for (uint32_t k = 0; k < KPR; k++)
-                        tab16_max<0>(tab_s32, hreg[k], t0 + r * C_ROUND + k * P_TEAM + ttid + 1);
+                        if (hreg[k] != 0xFFFFFFFFu) atomicMax(&S.tab[hreg[k]], t0 + r * C_ROUND + k * P_TEAM + ttid + 1);
                     TEAM_A_SYNC();
                 }
                 if (lane == 0 && anyM) atomicOr(&S.a_any[b], 1u);
@@ -213,7 +192,7 @@ lz4_blocks_pipe_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32
                 const bool do_parse = !((!tile_has_match && !e_din) || e >= t1);
                 if (!do_parse) { if (e < t1) e = t1; if (ttid == 0) T.do_parse = 0; }
                 else {
-                    PipeView W{S.in, T.off, T.len, T.M, T.V, S.Sel, S.Cont, S.xfree, S.xdin, S.link, S.mpos, S.longl, S.nlong};
+                    PipeView W{S.in, T.off, nullptr, T.M, T.V, S.Sel, S.Cont, S.xfree, S.xdin, S.link, S.mpos, S.longl, S.nlong};
                     const uint32_t k0 = (e - t0) / C_SEG;
                     const uint32_t seg0 = t0 + ttid * C_SEG;
                     const bool alive = ttid >= k0;
@@ -229,18 +208,18 @@ lz4_blocks_pipe_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32
                     uint32_t pm = (1u << lane) | (1u << jmp);
 #pragma unroll
                     for (int r = 0; r < 5; r++) { pm |= __shfl_sync(ZMT_FULL_MASK, pm, jmp); jmp = __shfl_sync(ZMT_FULL_MASK, jmp, jmp); }
-                    S.jump[ttid] = (uint16_t)(32 * twid + jmp);
+                    S.jump[ttid] = (uint8_t)(32 * twid + jmp);
                     S.xfree[ttid] = pm;
                     if (ttid < 8) S.entry[ttid] = 0xFFFFu;
                     TEAM_A_SYNC();
                     if (ttid == 0) {
                         uint32_t cur = k0;
-                        T.min_[k0] = (uint16_t)(e - t0);
+                        T.min_[k0] = (uint8_t)((e - t0) & (C_SEG - 1));
                         for (;;) {
                             S.entry[cur >> 5] = (uint16_t)cur;
                             const uint32_t t = S.jump[cur], tl = S.link[t];
                             if (tl == C_END) { S.e_next = S.mpos[t]; S.d_next = S.xdin[t]; break; }
-                            T.min_[tl] = (uint16_t)(S.mpos[t] - t0);
+                            T.min_[tl] = (uint8_t)((S.mpos[t] - t0) & (C_SEG - 1));
                             cur = tl;
                         }
                         T.k0 = k0; T.e_din = e_din; T.do_parse = 1;
@@ -249,7 +228,7 @@ lz4_blocks_pipe_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32
                     const uint32_t a = S.entry[twid];
                     const uint32_t pmask = (a != 0xFFFFu) ? S.xfree[a] : 0u;
                     if (lane == 0) T.pathmask[twid] = pmask;
-                    if (((pmask >> lane) & 1u) && inwarp) T.min_[lk] = (uint16_t)(S.mpos[ttid] - t0);
+                    if (((pmask >> lane) & 1u) && inwarp) T.min_[lk] = (uint8_t)((S.mpos[ttid] - t0) & (C_SEG - 1));
                     e = S.e_next; e_din = S.d_next;
                 }
                 if (b) bar_arrive<PB_FULL0 + 1, 2 * P_TEAM>(); else bar_arrive<PB_FULL0, 2 * P_TEAM>();
@@ -261,13 +240,13 @@ lz4_blocks_pipe_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32
             for (uint32_t ti = 0; ti < ntiles; ti++) {
                 const uint32_t t0 = ti * C_TILE, b = ti & 1;
                 PipeTile& T = S.tile[b];
-                PipeView W{S.in, T.off, T.len, T.M, T.V, S.Sel, S.Cont, S.xfree, S.xdin, S.link, S.mpos, S.longl, S.nlong};
+                PipeView W{S.in, T.off, S.len, T.M, T.V, S.Sel, S.Cont, S.xfree, S.xdin, S.link, S.mpos, S.longl, S.nlong};
                 if (b) bar_sync<PB_FULL0 + 1, 2 * P_TEAM>(); else bar_sync<PB_FULL0, 2 * P_TEAM>();
                 if (T.do_parse) do {
                     const uint32_t k0 = T.k0;
                     if (ttid < C_TILE / 32) { S.Sel[ttid] = 0; S.Cont[ttid] = 0; }
                     TEAM_B_SYNC();
-                    if ((T.pathmask[twid] >> lane) & 1u) c_walk<2>(W, ttid, t0 + T.min_[ttid], ttid == k0 ? T.e_din : 0u, t0, limit);
+                    if ((T.pathmask[twid] >> lane) & 1u) c_walk<2>(W, ttid, t0 + ttid * C_SEG + T.min_[ttid], ttid == k0 ? T.e_din : 0u, t0, limit);
                     TEAM_B_SYNC();
                     uint32_t np;
                     {
@@ -278,7 +257,7 @@ lz4_blocks_pipe_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32
                     TEAM_B_SYNC();
                     if (np == 0) break;
                     uint32_t nh_local = 0, headmask = 0;
-                    constexpr uint32_t PPT = C_MAXPIECE / P_TEAM;
+                    constexpr uint32_t PPT = P_MAXPIECE / P_TEAM;
 #pragma unroll
                     for (uint32_t k = 0; k < PPT; k++) {
                         const uint32_t r = ttid * PPT + k;
@@ -290,7 +269,7 @@ lz4_blocks_pipe_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32
                                 if (r == 0) { pend = pd_valid ? pd_end : 0xFFFFFFFFu; poff = pd_off; }
                                 else {
                                     uint32_t q = r - 1, pb = S.piece[q];
-                                    pend = t0 + pb + T.len[pb];
+                                    pend = t0 + pb + S.len[pb];
                                     while (((S.Cont[pb >> 5] >> (pb & 31)) & 1) && q > 0) { q--; pb = S.piece[q]; }
                                     poff = ((S.Cont[pb >> 5] >> (pb & 31)) & 1) ? pd_off : T.off[pb];
                                 }
@@ -307,9 +286,9 @@ lz4_blocks_pipe_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32
                     }
                     TEAM_B_SYNC();
                     const uint32_t lastp = S.piece[np - 1];
-                    const uint32_t tile_end = t0 + lastp + T.len[lastp];
+                    const uint32_t tile_end = t0 + lastp + S.len[lastp];
                     if (nh == 0) { pd_end = tile_end; break; }
-                    if (pd_valid && S.hidx[0] > 0) { const uint32_t pb = S.piece[S.hidx[0] - 1]; pd_end = t0 + pb + T.len[pb]; }
+                    if (pd_valid && S.hidx[0] > 0) { const uint32_t pb = S.piece[S.hidx[0] - 1]; pd_end = t0 + pb + S.len[pb]; }
                     const uint32_t nemit = pd_valid + nh - 1;
                     constexpr uint32_t SPT = 1024 / P_TEAM;
                     uint32_t sz = 0, e_lit0[SPT], e_lit[SPT], e_off[SPT], e_len[SPT], cnt = 0;
@@ -323,9 +302,9 @@ lz4_blocks_pipe_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32
                                 const uint32_t h = sidx - pd_valid;
                                 const uint32_t pi = S.hidx[h], pr = S.piece[pi];
                                 const uint32_t pl = S.piece[S.hidx[h + 1] - 1];
-                                st = t0 + pr; of = T.off[pr]; en = t0 + pl + T.len[pl];
+                                st = t0 + pr; of = T.off[pr]; en = t0 + pl + S.len[pl];
                                 if (h == 0) ls = pd_valid ? pd_end : pd_lit;
-                                else { const uint32_t pp = S.piece[pi - 1]; ls = t0 + pp + T.len[pp]; }
+                                else { const uint32_t pp = S.piece[pi - 1]; ls = t0 + pp + S.len[pp]; }
                             }
                             e_lit0[k] = ls; e_lit[k] = st - ls; e_off[k] = of; e_len[k] = en - st;
                             sz += c_seq_size(e_lit[k], e_len[k]); cnt++;
@@ -342,13 +321,13 @@ lz4_blocks_pipe_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32
                     {
                         const uint32_t nl = S.nlong;
                         for (uint32_t s = twid; s < nl; s += P_TEAM / 32) {
-                            const uint32_t sp = S.longl[3 * s], dp = S.longl[3 * s + 1], ln = S.longl[3 * s + 2];
+                            const uint32_t sl = S.longl[2 * s], dp = S.longl[2 * s + 1], sp = sl & 0xFFFFu, ln = sl >> 16;
                             for (uint32_t i = lane; i < ln; i += 32) dst[dp + i] = S.in[sp + i];
                         }
                         out_pos += total;
                         const uint32_t pi = S.hidx[nh - 1], pr = S.piece[pi];
                         uint32_t ls;
-                        if (nh >= 2 || pd_valid) { if (pi > 0) { const uint32_t pp = S.piece[pi - 1]; ls = t0 + pp + T.len[pp]; } else ls = pd_end; }
+                        if (nh >= 2 || pd_valid) { if (pi > 0) { const uint32_t pp = S.piece[pi - 1]; ls = t0 + pp + S.len[pp]; } else ls = pd_end; }
                         else ls = pd_lit;
                         pd_valid = 1; pd_lit = ls; pd_start = t0 + pr; pd_off = T.off[pr]; pd_end = tile_end;
                         TEAM_B_SYNC();
@@ -360,14 +339,14 @@ lz4_blocks_pipe_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32
             // ---- flush the pending sequence
             uint32_t anchor = 0;
             if (pd_valid) {
-                PipeView W{S.in, S.tile[0].off, S.tile[0].len, S.tile[0].M, S.tile[0].V, S.Sel, S.Cont, S.xfree, S.xdin, S.link, S.mpos, S.longl, S.nlong};
+                PipeView W{S.in, S.tile[0].off, S.len, S.tile[0].M, S.tile[0].V, S.Sel, S.Cont, S.xfree, S.xdin, S.link, S.mpos, S.longl, S.nlong};
                 anchor = pd_end;
                 TEAM_B_SYNC();                                 // S.nlong = 0 of the last tile is visible
                 if (ttid == 0) (void)c_emit_seq(W, dst, out_pos, pd_lit, pd_start - pd_lit, pd_off, pd_end - pd_start);
                 out_pos += c_seq_size(pd_start - pd_lit, pd_end - pd_start);
                 TEAM_B_SYNC();
                 if (S.nlong) {
-                    const uint32_t sp = S.longl[0], dp = S.longl[1], ln = S.longl[2];
+                    const uint32_t sl = S.longl[0], dp = S.longl[1], sp = sl & 0xFFFFu, ln = sl >> 16;
                     for (uint32_t i = ttid; i < ln; i += P_TEAM) dst[dp + i] = S.in[sp + i];
                 }
             }
