@@ -180,17 +180,44 @@ __device__ __forceinline__ uint32_t c_emit_seq(SM& S, uint8_t* dst, uint32_t o, 
     uint8_t* op = dst + o;
     const uint32_t ml = mlen - 4;
     *op++ = (uint8_t)(((lit >= 15 ? 15u : lit) << 4) | (ml >= 15 ? 15u : ml));
+    if (SM::relen) {
+        // pipelined kernel: no serial 255-runs.  The 255 bytes of a literal length exist only when lit >= 270 > C_LONGLIT
+        // and are written by the warp that copies that literal run; long match-length runs become a fill job.
+        static_assert(C_LONGLIT < 15 + 255, "literal-length 255 runs must imply the cooperative path");
+        if (lit >= 15) { const uint32_t x = lit - 15, nf = x / 255; op += nf; *op++ = (uint8_t)(x - nf * 255); }
+        if (lit <= C_LONGLIT) { for (uint32_t i = 0; i < lit; i++) op[i] = S.in[lit_start + i]; }
+        else { const uint32_t s = atomicAdd(&S.nlong, 1u); S.longl[2 * s] = lit_start | (lit << 16); S.longl[2 * s + 1] = (uint32_t)(op - dst); }
+        op += lit;
+        *op++ = (uint8_t)off; *op++ = (uint8_t)(off >> 8);
+        if (ml >= 15) {
+            const uint32_t x = ml - 15, nf = x / 255;
+            if (nf > 4) { const uint32_t s = atomicAdd(&S.nlong, 1u); S.longl[2 * s] = nf; S.longl[2 * s + 1] = (uint32_t)(op - dst) | 0x80000000u; op += nf; }
+            else for (uint32_t i = 0; i < nf; i++) *op++ = 255;
+            *op++ = (uint8_t)(x - nf * 255);
+        }
+        return (uint32_t)(op - (dst + o));
+    }
     if (lit >= 15) { uint32_t x = lit - 15; while (x >= 255) { *op++ = 255; x -= 255; } *op++ = (uint8_t)x; }
     if (lit <= C_LONGLIT) { for (uint32_t i = 0; i < lit; i++) op[i] = S.in[lit_start + i]; }
-    else {
-        const uint32_t s = atomicAdd(&S.nlong, 1u);
-        if (SM::relen) { S.longl[2 * s] = lit_start | (lit << 16); S.longl[2 * s + 1] = (uint32_t)(op - dst); }     // pipelined kernel: packed (both < 65536)
-        else { S.longl[3 * s] = lit_start; S.longl[3 * s + 1] = (uint32_t)(op - dst); S.longl[3 * s + 2] = lit; }
-    }
+    else { const uint32_t s = atomicAdd(&S.nlong, 1u); S.longl[3 * s] = lit_start; S.longl[3 * s + 1] = (uint32_t)(op - dst); S.longl[3 * s + 2] = lit; }
     op += lit;
     *op++ = (uint8_t)off; *op++ = (uint8_t)(off >> 8);
     if (ml >= 15) { uint32_t x = ml - 15; while (x >= 255) { *op++ = 255; x -= 255; } *op++ = (uint8_t)x; }
     return (uint32_t)(op - (dst + o));
+}
+
+// pipelined kernel: one job of the long list, done by `nthr` threads (thread index t): a literal run with the 255 bytes
+// of its length field, or a run of 255 bytes of a match length
+template <class SM>
+__device__ __forceinline__ void c_long_job(SM& S, uint8_t* dst, uint32_t s, uint32_t t, uint32_t nthr)
+{
+    const uint32_t a = S.longl[2 * s], dp = S.longl[2 * s + 1];
+    if (dp & 0x80000000u) { uint8_t* q = dst + (dp & 0x7FFFFFFFu); for (uint32_t i = t; i < a; i += nthr) q[i] = 255; return; }
+    const uint32_t sp = a & 0xFFFFu, ln = a >> 16;
+    for (uint32_t i = t; i < ln; i += nthr) dst[dp + i] = S.in[sp + i];
+    const uint32_t nf = (ln - 15) / 255;                       // ln > C_LONGLIT >= 15
+    uint8_t* q = dst + dp - 1 - nf;
+    for (uint32_t i = t; i < nf; i += nthr) q[i] = 255;
 }
 
 // CODEC 0: LZ4 block format out.  CODEC 1: Zstandard blocks out (same candidates + parse, entropy stage per ~16 KiB).

@@ -69,7 +69,8 @@ struct __align__(16) PipeSmem {
     uint8_t  len[C_TILE];                 // piece length per selected piece start (written by the marking walk)
     uint16_t piece[P_MAXPIECE];
     uint16_t hidx[C_TILE / 4];            // heads: one per sequence, sequences hold a match of >= 4 bytes
-    uint32_t longl[2 * (C_TILE / (C_LONGLIT + 1) + 2)];   // (start | length << 16, output offset) of literal runs > C_LONGLIT
+    uint32_t longl[2 * (C_TILE / (C_LONGLIT + 1) + 2)];   // jobs: literal runs > C_LONGLIT (start | length << 16, output offset) -- at most
+                                                           // 4096/37 + 1 pending per tile -- and 255-runs of match lengths >= 1290 (count, offset | 1<<31)
     __align__(16) uint32_t scanws[16];
     uint32_t nlong;
     uint32_t fin_anchor, fin_out;
@@ -320,10 +321,7 @@ lz4_blocks_pipe_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32
                     TEAM_B_SYNC();
                     {
                         const uint32_t nl = S.nlong;
-                        for (uint32_t s = twid; s < nl; s += P_TEAM / 32) {
-                            const uint32_t sl = S.longl[2 * s], dp = S.longl[2 * s + 1], sp = sl & 0xFFFFu, ln = sl >> 16;
-                            for (uint32_t i = lane; i < ln; i += 32) dst[dp + i] = S.in[sp + i];
-                        }
+                        for (uint32_t s = twid; s < nl; s += P_TEAM / 32) c_long_job(W, dst, s, lane, 32u);
                         out_pos += total;
                         const uint32_t pi = S.hidx[nh - 1], pr = S.piece[pi];
                         uint32_t ls;
@@ -345,10 +343,8 @@ lz4_blocks_pipe_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32
                 if (ttid == 0) (void)c_emit_seq(W, dst, out_pos, pd_lit, pd_start - pd_lit, pd_off, pd_end - pd_start);
                 out_pos += c_seq_size(pd_start - pd_lit, pd_end - pd_start);
                 TEAM_B_SYNC();
-                if (S.nlong) {
-                    const uint32_t sl = S.longl[0], dp = S.longl[1], sp = sl & 0xFFFFu, ln = sl >> 16;
-                    for (uint32_t i = ttid; i < ln; i += P_TEAM) dst[dp + i] = S.in[sp + i];
-                }
+                const uint32_t nl = S.nlong;                            // long literal run and / or long match length of the pending sequence
+                for (uint32_t s = 0; s < nl; s++) c_long_job(W, dst, s, ttid, P_TEAM);
             }
             if (ttid == 0) { S.fin_anchor = anchor; S.fin_out = out_pos; }
         }
@@ -362,10 +358,11 @@ lz4_blocks_pipe_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32
                 uint8_t* op = dst + out_pos;
                 uint32_t hl = 1;
                 if (lit >= 15) hl += 1 + (lit - 15) / 255;
+                const uint32_t nf = lit >= 15 ? (lit - 15) / 255 : 0;
+                for (uint32_t i = tid; i < nf; i += NT) op[1 + i] = 255;
                 if (tid == 0) {
-                    uint8_t* q = op;
-                    *q++ = (uint8_t)((lit >= 15 ? 15u : lit) << 4);
-                    if (lit >= 15) { uint32_t x = lit - 15; while (x >= 255) { *q++ = 255; x -= 255; } *q++ = (uint8_t)x; }
+                    op[0] = (uint8_t)((lit >= 15 ? 15u : lit) << 4);
+                    if (lit >= 15) op[1 + nf] = (uint8_t)(lit - 15 - nf * 255);
                     blk_csize[blk] = fin;
                 }
                 for (uint32_t i = tid; i < lit; i += NT) op[hl + i] = S.in[anchor + i];
