@@ -5,7 +5,8 @@
 // /root/reference/lib/zstd-mt_compress.c:284-286:
 //   literals  : raw / RLE / Huffman (4 streams, tree described by direct 4-bit weights)
 //   sequences : LL / OF / ML codes + extra bits on the PREDEFINED FSE tables (mode 0,0,0), the three state
-//               chains run on three lanes, every bit field is then placed in parallel from a scan of bit counts
+//               chains run chunk-parallel on the 32 lanes of one warp (speculative entry states, verified),
+//               every bit field is then placed in parallel from a scan of bit counts
 //   block     : 3-byte header, raw fallback when nothing is gained
 // Every block is self-contained (own Huffman tree, predefined sequence tables, explicit offsets: no repeat
 // codes), so the decoder can give each block its own CTA.
@@ -16,6 +17,7 @@
 #define Z_MAXLIT     (40u * 1024u)   // literal bytes per sub-block (16 KiB of tiles + up to ~16 KiB carried + slack)
 #define Z_BITWORDS   3072u           // shared bit buffer: 12 KiB
 #define Z_HUF_MAXBITS 11
+#define Z_WARM        16u             // warm-up symbols of a speculative FSE chain chunk
 
 struct __align__(8) ZSeq { uint32_t litlen; uint16_t off; uint16_t mlen; };
 
@@ -42,6 +44,7 @@ struct ZEnt {
     uint32_t seqbits, fin[3];        // final FSE states
     uint8_t  wdesc[136];             // Huffman tree description when coded with FSE (header byte + <= 127 bytes)
     uint32_t wdesc_len;
+    uint8_t  codes[Z_MAXSEQ];        // symbol codes of the stream the chain warp is working on, in encoding order
 };
 
 // ---- predefined-distribution FSE encoding tables (filled by the host once per device: zstd_tables_init)
@@ -227,42 +230,59 @@ __device__ uint32_t z_encode_block(ZEnt& Z, const ZFseShared& F, ZScratch* zs, u
 
     if (wid == 7) {
         // ------------------------------------------------------------ FSE state chains
-        // Encoding order is last sequence first (RFC 8878 §3.1.1.3.2.1.1: the decoder reads backwards).  The chains are
-        // serial in the FSE state; everything else is off their critical path: the warp fetches 32 sequence records
-        // at a time (coalesced), every lane turns its record into the three symbol codes, the codes reach chain
-        // lanes 0 (LL), 1 (OF), 2 (ML) by shuffle one step ahead, tables sit in shared memory.
+        // Encoding order is last sequence first (RFC 8878 §3.1.1.3.2.1.1: the decoder reads backwards); step t encodes
+        // sequence nseq-1-t.  A chain is serial in its state, but FSE states re-synchronise quickly: the state after a
+        // symbol lies in that symbol's sub-range of the table (one value for the many symbols of probability 1/64),
+        // whatever the state before.  So the 32 lanes each take a contiguous chunk of steps: a lane warms up over
+        // the Z_WARM steps before its chunk from an arbitrary valid state (exact when the warm-up reaches step 0),
+        // runs its chunk, and the warp then checks every chunk's entry state against its predecessor's exit state and
+        // re-runs the (rare) chunks that guessed wrong until nothing changes.  Same bits as the serial chain,
+        // ~nseq/32 + Z_WARM serial steps per stream instead of nseq.  One stream at a time: the symbol codes of the
+        // current stream sit in shared memory (Z.codes), the (nbBits, value) pairs go to the scratch as before.
         if (nseq) {
-            const uint32_t kk = lane < 3 ? lane : 0;
-            uint32_t st = 0;
-            for (int hi = (int)nseq - 1; hi >= 0; hi -= 32) {
-                const int idx = hi - (int)lane;              // lane 0 holds the record processed first
-                uint32_t packed = 0;
-                if (idx >= 0) {
+            const uint32_t c = (nseq + 31) / 32;
+            const uint32_t t_begin = lane * c, t_end = t_begin + c < nseq ? t_begin + c : nseq;
+            const bool have = t_begin < nseq;
+            const uint32_t w0 = t_begin > Z_WARM ? t_begin - Z_WARM : 0;
+            for (uint32_t kk = 0; kk < 3; kk++) {
+                __syncwarp();
+                for (uint32_t idx = lane; idx < nseq; idx += 32) {
                     const ZSeq q = zs->seq[idx];
-                    packed = z_ll_code(q.litlen) | (z_highbit((uint32_t)q.off + 3u) << 8) | (z_ml_code((uint32_t)q.mlen - 3u) << 16);
+                    const uint32_t code = kk == 0 ? z_ll_code(q.litlen) : kk == 1 ? z_highbit((uint32_t)q.off + 3u) : z_ml_code((uint32_t)q.mlen - 3u);
+                    Z.codes[nseq - 1 - idx] = (uint8_t)code;
                 }
-                const int cnt = hi + 1 < 32 ? hi + 1 : 32;
-                uint32_t pk = __shfl_sync(ZMT_FULL_MASK, packed, 0);
-                int2 tt = F.tt[kk][(pk >> (8 * kk)) & 0xFF];
-                for (int jj = 0; jj < cnt; jj++) {
-                    const int2 cur = tt;
-                    const uint32_t pkn = __shfl_sync(ZMT_FULL_MASK, packed, (jj + 1) & 31);      // next step's symbol + table entry
-                    tt = F.tt[kk][(pkn >> (8 * kk)) & 0xFF];
-                    if (lane < 3) {
+                __syncwarp();
+                const int2* const TT = F.tt[kk];
+                const uint16_t* const ST = F.state[kk];
+                // FSE_initCState2: the state "after" a first symbol, no bits
+                auto init_state = [&](int2 tt) -> uint32_t { const uint32_t nbo = (uint32_t)(tt.x + (1 << 15)) >> 16; return ST[(((nbo << 16) - (uint32_t)tt.x) >> nbo) + tt.y]; };
+                uint32_t sin = 0;
+                if (have) {
+                    sin = init_state(TT[Z.codes[w0]]);
+                    for (uint32_t t = w0 + 1; t < t_begin; t++) { const int2 tt = TT[Z.codes[t]]; const uint32_t nbo = (sin + (uint32_t)tt.x) >> 16; sin = ST[(sin >> nbo) + tt.y]; }
+                }
+                auto run_chunk = [&](uint32_t st) -> uint32_t {
+#pragma unroll 4
+                    for (uint32_t t = t_begin; t < t_end; t++) {
+                        const int2 tt = TT[Z.codes[t]];
                         uint32_t outv = 0;
-                        if (hi == (int)nseq - 1 && jj == 0) {    // FSE_initCState2: start state from the last sequence's symbol, no bits
-                            const uint32_t nbo = (uint32_t)(cur.x + (1 << 15)) >> 16;
-                            st = F.state[kk][(((nbo << 16) - (uint32_t)cur.x) >> nbo) + cur.y];
-                        } else {
-                            const uint32_t nbo = (st + (uint32_t)cur.x) >> 16;
-                            outv = (nbo << 16) | (st & ((1u << nbo) - 1));
-                            st = F.state[kk][(st >> nbo) + cur.y];
-                        }
-                        zs->fse[kk][hi - jj] = outv;
+                        if (t == 0) st = init_state(tt);
+                        else { const uint32_t nbo = (st + (uint32_t)tt.x) >> 16; outv = (nbo << 16) | (st & ((1u << nbo) - 1)); st = ST[(st >> nbo) + tt.y]; }
+                        zs->fse[kk][nseq - 1 - t] = outv;
                     }
+                    return st;
+                };
+                uint32_t sout = have ? run_chunk(sin) : 0;
+                for (;;) {                                   // repair chunks whose speculative entry state was wrong
+                    const uint32_t prev = __shfl_up_sync(ZMT_FULL_MASK, sout, 1);
+                    const bool bad = have && lane > 0 && prev != sin;
+                    if (!__any_sync(ZMT_FULL_MASK, bad)) break;
+                    if (bad) { sin = prev; sout = run_chunk(sin); }
+                    __syncwarp();
                 }
+                const uint32_t fin = __shfl_sync(ZMT_FULL_MASK, sout, (nseq - 1) / c);
+                if (lane == 0) Z.fin[kk] = fin;
             }
-            if (lane < 3) Z.fin[lane] = st;
         }
     } else {
         // ------------------------------------------------------------ literal pipeline (224 threads)
