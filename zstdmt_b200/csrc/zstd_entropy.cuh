@@ -129,9 +129,11 @@ __device__ uint32_t z_fse_weights(ZEnt& Z, uint32_t nw /* weights listed = maxsy
         }
     }
     // ---- NCount header (forward bit order)
+    // bits are gathered in a register and leave as whole bytes (a bit-at-a-time read-modify-write of shared memory made
+    // this single-thread step the longest wait of the literal pipeline)
     uint8_t* out = Z.wdesc + 1; uint32_t bitpos = 0;
-    for (int i = 0; i < 135; i++) Z.wdesc[i] = 0;
-    auto put = [&](uint32_t v, uint32_t nb) { for (uint32_t k = 0; k < nb; k++, bitpos++) if ((v >> k) & 1) out[bitpos >> 3] |= (uint8_t)(1u << (bitpos & 7)); };
+    uint64_t acc = 0; uint32_t nacc = 0; uint8_t* wp = out;
+    auto put = [&](uint32_t v, uint32_t nb) { acc |= (uint64_t)(v & ((1u << nb) - 1)) << nacc; nacc += nb; bitpos += nb; while (nacc >= 8) { *wp++ = (uint8_t)acc; acc >>= 8; nacc -= 8; } };
     put((uint32_t)(LOG - 5), 4);
     {
         int remaining = SIZE + 1, threshold = SIZE, nbBits = LOG + 1; uint32_t sym = 0; bool prev0 = false;
@@ -155,6 +157,7 @@ __device__ uint32_t z_fse_weights(ZEnt& Z, uint32_t nw /* weights listed = maxsy
         }
         if (remaining != 1) return 0;
     }
+    if (nacc) { *wp++ = (uint8_t)acc; }
     const uint32_t hdr_bytes = (bitpos + 7) >> 3;
     // ---- encoding table (FSE_buildCTable)
     {
@@ -171,19 +174,25 @@ __device__ uint32_t z_fse_weights(ZEnt& Z, uint32_t nw /* weights listed = maxsy
         }
     }
     // ---- two interleaved states, last weight first (FSE_compress_usingCTable_generic)
+    if (hdr_bytes >= 100) return 0;
     uint8_t* bs = out + hdr_bytes; uint32_t bpos = 0;
     const uint32_t bcap = (127 - hdr_bytes) * 8;                     // the FSE form must fit 127 bytes (header byte < 128)
     bool over = false;
-    auto putb = [&](uint32_t v, uint32_t nb) { for (uint32_t k = 0; k < nb; k++, bpos++) { if (bpos >= bcap) { over = true; return; } if ((v >> k) & 1) bs[bpos >> 3] |= (uint8_t)(1u << (bpos & 7)); } };
+    acc = 0; nacc = 0; wp = bs;
+    auto putb = [&](uint32_t v, uint32_t nb) {
+        if (bpos + nb > bcap) { over = true; return; }
+        acc |= (uint64_t)(v & ((1u << nb) - 1)) << nacc; nacc += nb; bpos += nb;
+        while (nacc >= 8) { *wp++ = (uint8_t)acc; acc >>= 8; nacc -= 8; }
+    };
     auto init = [&](uint32_t sy) -> uint32_t { const uint32_t nbo = (uint32_t)(dnb[sy] + (1 << 15)) >> 16; return stab[(((nbo << 16) - (uint32_t)dnb[sy]) >> nbo) + dfs[sy]]; };
     auto enc = [&](uint32_t& st, uint32_t sy) { const uint32_t nbo = (st + (uint32_t)dnb[sy]) >> 16; putb(st & ((1u << nbo) - 1), nbo); st = stab[(st >> nbo) + dfs[sy]]; };
-    if (hdr_bytes >= 100) return 0;
     int ip = (int)nw; uint32_t s1, s2;
     if (nw & 1) { s1 = init(wt[--ip]); s2 = init(wt[--ip]); enc(s1, wt[--ip]); }
     else { s2 = init(wt[--ip]); s1 = init(wt[--ip]); }
     while (ip > 0) { enc(s2, wt[--ip]); enc(s1, wt[--ip]); }
     putb(s2, (uint32_t)LOG); putb(s1, (uint32_t)LOG);
     putb(1, 1);
+    if (nacc) *wp++ = (uint8_t)acc;
     const uint32_t total_bytes = hdr_bytes + ((bpos + 7) >> 3);
     if (over || total_bytes >= 128) return 0;
     Z.wdesc[0] = (uint8_t)total_bytes;
