@@ -51,30 +51,36 @@ __constant__ uint32_t d_ll_base[36], d_ml_base[53];
 __constant__ uint8_t  d_ll_bits[36], d_ml_bits[53];
 
 // ---------------------------------------------------------------- backward bit reader over global memory
-// bit `off` = number of unread bits; reads below the stream start return zeros (off goes negative = exhausted)
+// bit `off` = number of unread bits; reads below the stream start return zeros (off goes negative = exhausted).
+// A 64-bit window of the stream (bits [wbit, wbit + 64)) lives in registers and is refilled with eight byte loads
+// when a read would fall below it — about once per 56 bits instead of four byte loads per read.
 struct BackBits {
-    const uint8_t* p; int32_t off;
+    const uint8_t* p; int32_t off; int32_t wbit; uint64_t win;
     __device__ __forceinline__ bool init(const uint8_t* s, uint32_t n)
     {
         if (n == 0) return false;
         const uint32_t lastb = s[n - 1];
         if (lastb == 0) return false;
         p = s; off = (int32_t)(n * 8) - (int32_t)(__clz(lastb) - 24 + 1);
+        wbit = 0x7FFFFFFF; win = 0;                      // empty window: the first read refills
         return true;
     }
-    // up to 25 bits
+    // up to 32 bits
     __device__ __forceinline__ uint32_t read(uint32_t nb)
     {
         if (nb == 0) return 0;
+        const int32_t top = off;                         // bits [top - nb, top); may reach below 0
         off -= (int32_t)nb;
-        const int32_t start = off;                       // may be negative
-        const int32_t byte0 = start >= 0 ? (start >> 3) : -((-start + 7) >> 3);
-        const int32_t sh = start - byte0 * 8;            // 0..7
-        uint32_t v = 0;
+        if (off < wbit) {
+            const int32_t tb = (top + 7) >> 3;           // window = the 8 bytes ending with the byte that holds bit top-1 (floor for negatives)
+            const int32_t b0 = tb - 8;
+            uint64_t w = 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++) { const int32_t b = byte0 + k; if (b >= 0) v |= (uint32_t)p[b] << (8 * k); }
+            for (int k = 0; k < 8; k++) { const int32_t b = b0 + k; if (b >= 0) w |= (uint64_t)p[b] << (8 * k); }
+            win = w; wbit = b0 * 8;
+        }
         // bits above the stream end never matter: callers only ask for bits that exist or pad below the start
-        return (v >> sh) & ((1u << nb) - 1);
+        return (uint32_t)(win >> (off - wbit)) & (nb >= 32 ? 0xFFFFFFFFu : ((1u << nb) - 1));
     }
 };
 
@@ -483,32 +489,57 @@ zstd_execute_kernel(const uint8_t* __restrict__ in, const ZBlk* __restrict__ blo
         uint32_t op = 0, lp = 0;
         bool bad = false;
         uint32_t waited_to = b;                              // blocks [waited_to, b) are known complete
-        for (uint32_t i = 0; i < B.nseq; i++) {
-            const ZDSeq q = seqs[i];
-            if ((uint64_t)op + q.ll + q.ml > rg || lp + q.ll > B.regen_hint) { bad = true; break; }
-            for (uint32_t k = lane; k < q.ll; k += 32) dst[op + k] = lit[lp + k];
-            op += q.ll; lp += q.ll;
-            const uint64_t abs_pos = (blk_out[b] - frame_base) + op;
-            if (q.off == 0 || q.off > abs_pos) { bad = true; break; }
-            if (q.off > op) {
-                // the match starts below this block: every earlier block it touches must be finished
-                const uint64_t need = blk_out[b] + op - q.off;                   // absolute output address of the first source byte
-                while (waited_to > 0 && blocks[waited_to - 1].frame == B.frame && blk_out[waited_to - 1] + regen[waited_to - 1] > need) {
-                    waited_to--;
-                    if (lane == 0) { while (vdone[waited_to] == 0) __nanosleep(64); }
-                }
-                __syncwarp();
-                __threadfence();
+        const uint64_t blk_abs = blk_out[b];                 // absolute output address of this block
+        const uint64_t blk_in_frame = blk_abs - frame_base;
+        // 32 sequences at a time: one coalesced load of the records, positions from two warp scans, every lane copies
+        // its own literal run (literals come from the scratch, not from the output: no ordering among them), then the
+        // matches run in sequence order with the whole warp on each copy.  Per sequence this leaves one dependent
+        // global read (the match source) on the critical path instead of three (record, literals, match).
+        for (uint32_t base = 0; base < B.nseq; base += 32) {
+            const uint32_t cnt = B.nseq - base < 32 ? B.nseq - base : 32;
+            uint32_t ll = 0, off = 0, ml = 0;
+            if (lane < cnt) { const ZDSeq q = seqs[base + lane]; ll = q.ll; off = q.off; ml = q.ml; }
+            uint32_t it = ll + ml, il = ll;                  // inclusive scans: output bytes, literal bytes
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, it, d), c = __shfl_up_sync(0xFFFFFFFFu, il, d);
+                if (lane >= (uint32_t)d) { it += a; il += c; }
+            }
+            const uint32_t my_op = op + it - (ll + ml), my_lp = lp + il - ll, my_mp = my_op + ll;
+            const bool mybad = lane < cnt && ((uint64_t)my_op + ll + ml > rg || (uint64_t)my_lp + ll > B.regen_hint || off == 0 || (uint64_t)off > blk_in_frame + my_mp);
+            const uint32_t badmask = __ballot_sync(0xFFFFFFFFu, mybad);
+            const uint32_t lim = badmask ? (uint32_t)(__ffs(badmask) - 1) : cnt;      // sequences of this batch that are executed
+            if (lane < lim && ll <= 32) { for (uint32_t k = 0; k < ll; k++) dst[my_op + k] = lit[my_lp + k]; }
+            uint32_t longmask = __ballot_sync(0xFFFFFFFFu, lane < lim && ll > 32);
+            while (longmask) {                                // long literal runs: the whole warp copies
+                const int jl = __ffs(longmask) - 1; longmask &= longmask - 1;
+                const uint32_t o = __shfl_sync(0xFFFFFFFFu, my_op, jl), l0 = __shfl_sync(0xFFFFFFFFu, my_lp, jl), n = __shfl_sync(0xFFFFFFFFu, ll, jl);
+                for (uint32_t k = lane; k < n; k += 32) dst[o + k] = lit[l0 + k];
             }
             __syncwarp();
-            uint8_t* d = dst + op;
-            const uint8_t* m = d - q.off;
-            const uint32_t ml = q.ml;
-            if (q.off >= ml) { for (uint32_t k = lane; k < ml; k += 32) d[k] = m[k]; }
-            else if (q.off >= 32) { for (uint32_t k = 0; k < ml; k += 32) { if (k + lane < ml) d[k + lane] = m[k + lane]; __syncwarp(); } }
-            else { for (uint32_t k = lane; k < ml; k += 32) d[k] = m[k % q.off]; }
-            op += ml;
-            __syncwarp();
+            for (uint32_t jq = 0; jq < lim; jq++) {
+                const uint32_t qoff = __shfl_sync(0xFFFFFFFFu, off, jq), qml = __shfl_sync(0xFFFFFFFFu, ml, jq), mp = __shfl_sync(0xFFFFFFFFu, my_mp, jq);
+                if (qoff > mp) {
+                    // the match starts below this block: every earlier block it touches must be finished
+                    const uint64_t need = blk_abs + mp - qoff;                      // absolute output address of the first source byte
+                    bool waited = false;
+                    while (waited_to > 0 && blocks[waited_to - 1].frame == B.frame && blk_out[waited_to - 1] + regen[waited_to - 1] > need) {
+                        waited_to--; waited = true;
+                        if (lane == 0) { while (vdone[waited_to] == 0) __nanosleep(64); }
+                    }
+                    __syncwarp();
+                    if (waited) __threadfence();
+                }
+                uint8_t* d = dst + mp;
+                const uint8_t* m = d - qoff;
+                if (qoff >= qml) { for (uint32_t k = lane; k < qml; k += 32) d[k] = m[k]; }
+                else if (qoff >= 32) { for (uint32_t k = 0; k < qml; k += 32) { if (k + lane < qml) d[k + lane] = m[k + lane]; __syncwarp(); } }
+                else { for (uint32_t k = lane; k < qml; k += 32) d[k] = m[k % qoff]; }
+                __syncwarp();
+            }
+            if (badmask) { bad = true; break; }
+            op += __shfl_sync(0xFFFFFFFFu, it, cnt - 1);
+            lp += __shfl_sync(0xFFFFFFFFu, il, cnt - 1);
         }
         if (!bad) {
             const uint32_t rest = B.regen_hint - lp;
