@@ -627,8 +627,11 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
     P.fill_seq = P.submit_seq = P.write_seq = 0; P.reader_done = false; P.error = 0;
     for (auto& s : P.slots) s.state = 0;
 
+    StageClock rd_clk, wr_clk; double rd_scan = 0, rd_total = 0, wr_total = 0;     // ZSTDMT_B200_TRACE=1
+    const bool tr = trace_on();
     // ---- reader (pt_read, lz4-mt_decompress.c:192-281 / zstd-mt_decompress.c:209-369)
     std::thread reader([&]() {
+        const double t_start = tr ? StageClock::now() : 0;
         bool eof = false;
         std::vector<uint8_t> carry;              // a frame that did not fit the previous slot
         uint64_t carry_out = 0;
@@ -637,7 +640,9 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
             {
                 std::unique_lock<std::mutex> lk(P.mu);
                 s = &P.slots[P.fill_seq % N];
+                const double t0 = tr ? StageClock::now() : 0;
                 P.cv.wait(lk, [&] { return s->state == 0 || P.error; });
+                if (tr) rd_clk.wait += StageClock::now() - t0;
                 if (P.error) break;
             }
             Tables T = tables_at(s->h_tab, s->tab_cap);
@@ -688,7 +693,9 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
                 else { carry.resize(12 + toRead); dstp = carry.data(); to_carry = true; }
                 memcpy(dstp, hdr, 12);
                 if (pre) memcpy(dstp + 12, first + 12, pre);
+                const double tc0 = tr ? StageClock::now() : 0;
                 size_t g = 0; size_t e = read_some(E, rw, dstp + 12 + pre, toRead - pre, &g);
+                if (tr) rd_clk.cb += StageClock::now() - tc0;
                 if (e) { P.fail(e); failed = true; break; }
                 if (g != toRead - pre) { P.fail(E.data_error); failed = true; break; }
                 stat_in += g;
@@ -699,7 +706,9 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
                 if (is_zstd) {
                     // block table of this frame (descriptors are appended; rolled back if the frame moves to the next batch)
                     uint64_t cs = 0;
+                    const double ts0 = tr ? StageClock::now() : 0;
                     int zr = zmt_zstd_scan_frame_host(dstp + 12, toRead, in_used + 12, n, s->h_blk, &nblk_new, s->blk_cap, &scr_new, &cs, &nsq);
+                    if (tr) rd_scan += StageClock::now() - ts0;
                     if (zr == ZMT_ST_DST_SMALL && n > 0) { carry.assign(dstp, dstp + 12 + toRead); carry_out = osz; break; }
                     if (zr != ZMT_ST_OK) { c->lib_errcode = (size_t)zr; P.fail(zr == ZMT_ST_TRUNCATED || zr == ZMT_ST_TRAILING ? E.frame_decompress : E.library); failed = true; break; }
                     if (scr_new > scr_cap && n > 0) { carry.assign(dstp, dstp + 12 + toRead); carry_out = osz; break; }
@@ -737,22 +746,28 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
             }
             P.cv.notify_all();
         }
+        if (tr) rd_total = StageClock::now() - t_start;
         { std::lock_guard<std::mutex> g(P.mu); P.reader_done = true; }
         P.cv.notify_all();
     });
 
     // ---- writer (pt_write, lz4-mt_decompress.c:165-187)
     std::thread writer([&]() {
+        const double t_start = tr ? StageClock::now() : 0;
         for (;;) {
             Slot* s;
             {
                 std::unique_lock<std::mutex> lk(P.mu);
                 s = &P.slots[P.write_seq % N];
+                const double t0 = tr ? StageClock::now() : 0;
                 P.cv.wait(lk, [&] { return s->state == 2 || P.error || (P.reader_done && P.write_seq == P.fill_seq); });
+                if (tr) wr_clk.wait += StageClock::now() - t0;
                 if (P.error || s->state != 2) break;
             }
             cudaSetDevice(s->dev);
+            const double tg0 = tr ? StageClock::now() : 0;
             if (cudaEventSynchronize(s->ev) != cudaSuccess) { c->lib_errcode = ZMT_ST_CUDA; P.fail(E.library); break; }
+            if (tr) wr_clk.gpu += StageClock::now() - tg0;
             Tables T = tables_at(s->h_tab, s->tab_cap);
             bool bad = false;
             for (uint32_t i = 0; i < s->n; i++) {
@@ -763,7 +778,9 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
                     bad = true; break;
                 }
                 GenBuffer b; b.buf = s->h_out + T.b[i]; b.size = (size_t)T.c[i]; b.allocated = b.size;
+                const double tc0 = tr ? StageClock::now() : 0;
                 int rv = rw->fn_write(rw->arg_write, &b);
+                if (tr) wr_clk.cb += StageClock::now() - tc0;
                 if (rv != 0) { P.fail(mt_error(E, rv)); bad = true; break; }
                 c->outsize += b.size; c->curframe++;
             }
@@ -803,6 +820,10 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
     }
     reader.join(); writer.join();
     for (auto& s : P.slots) { if (s.ok) { cudaSetDevice(s.dev); cudaStreamSynchronize(s.stream); } }
+    if (tr)
+        fprintf(stderr, "[zstdmt_b200] decompress: reader total %.3fs cb %.3fs scan %.3fs wait %.3fs | writer gpu-wait %.3fs cb %.3fs wait %.3fs | slots %zu, batch %zu MiB\n",
+                rd_total, rd_clk.cb, rd_scan, rd_clk.wait, wr_clk.gpu, wr_clk.cb, wr_clk.wait, N, in_cap0 >> 20);
+    (void)wr_total;
     return P.error;
 }
 
