@@ -15,7 +15,7 @@ for ln in out.splitlines():
     if not m: continue
     s, f, l = int(m.group(1)), m.group(3), int(m.group(4)); tot += s
     if f == "lz4_pipe.cuh":
-        if l < L["exscan"]: g = "barrier helpers / tab16_max"
+        if l < L["exscan"]: g = "barrier helpers (bar.sync / bar.arrive)"
         elif l < L["kern"]: g = "B: team_exscan1"
         elif l < L["teamA"]: g = "stage block (all)"
         elif l < L["rounds"]: g = "A: wait EMPTY + tile setup"
