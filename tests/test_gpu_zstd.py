@@ -99,6 +99,28 @@ def test_every_data_class_roundtrips(torch, first):
     assert not status.any() and np.array_equal(back, src)
 
 
+@pytest.mark.parametrize("run_len,seed", [(7196, 1), (5, 2), (30000, 3)])
+def test_pending_match_then_incompressible_tail(torch, run_len, seed):
+    """Regression (found by tools/stress_gpu.py): a window that starts with one long match and continues with
+    incompressible bytes keeps that match pending until the window ends, so no sub-block is closed on the way and the
+    final block carries up to 64 KiB of literals — more than the literal scratch used to hold (40 KiB)."""
+    rng = np.random.default_rng(seed)
+    win = []
+    for w in range(6):
+        head = rng.integers(0, 256, 1 + w, dtype=np.uint8)
+        run = np.full(run_len, int(head[-1]), np.uint8)
+        win.append(np.concatenate([head, run, rng.integers(0, 256, 65536 - head.size - run_len, dtype=np.uint8)]))
+    src = np.concatenate(win)
+    framed, foff = gpu_compress(torch, src, 1 << 20)
+    rc, back = o.orc_decode(o.CODEC_ZSTD, framed, src.size)
+    assert rc == 0 and np.array_equal(back, src)
+    if o.have_ref():
+        rc, b2, _ = o.ref_decompress(o.CODEC_ZSTD, framed, src.size, threads=1)
+        assert rc == 0 and np.array_equal(b2, src)
+    back, status, dec = gpu_decompress(torch, framed)
+    assert not status.any() and np.array_equal(back, src)
+
+
 def test_ratio_between_lz4_path_and_libzstd(torch):
     """Sanity: the entropy stage must buy something over the LZ4 container on text."""
     n = 8 << 20

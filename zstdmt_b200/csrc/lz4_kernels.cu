@@ -1152,7 +1152,8 @@ extern "C" int zmt_lz4_compress_device(const void* d_in, uint64_t in_bytes, uint
 }
 
 // ---------------------------------------------------------------- zstd compress
-static inline uint32_t zstd_grid(uint32_t nblocks) { const uint32_t m = (uint32_t)(zmt_sm_count() * 2 * 4); return nblocks < m ? nblocks : m; }
+#define ZSTD_MAX_GRID (148u * 2u * 4u)       // the workspace holds one ZScratch per CTA of the largest grid (B200: 148 SMs)
+static inline uint32_t zstd_grid(uint32_t nblocks) { uint32_t m = (uint32_t)(zmt_sm_count() * 2 * 4); if (m > ZSTD_MAX_GRID) m = ZSTD_MAX_GRID; return nblocks < m ? nblocks : m; }
 
 extern "C" size_t zmt_zstdc_workspace_bytes(uint32_t nchunks, uint32_t chunk_size)
 {
@@ -1162,7 +1163,7 @@ extern "C" size_t zmt_zstdc_workspace_bytes(uint32_t nchunks, uint32_t chunk_siz
     uint64_t sz = nblocks * ZMT_LZ4_TMP_STRIDE;
     sz += ((nblocks * 4 + 255) & ~255ull);
     sz += ((((uint64_t)nchunks + 1) * 8 + 255) & ~255ull);
-    sz += (uint64_t)(148 * 2 * 4 + 8) * ((sizeof(ZScratch) + 255) & ~255ull);      // per-CTA scratch, sized for the largest grid we launch
+    sz += (uint64_t)(ZSTD_MAX_GRID + 8) * ((sizeof(ZScratch) + 255) & ~255ull);    // per-CTA scratch, sized for the largest grid we launch
     return (size_t)sz + 1024;
 }
 

@@ -14,7 +14,8 @@
 #include "common.cuh"
 
 #define Z_MAXSEQ     4352u           // sequences per sub-block (4 tiles x 1024 + pending + slack)
-#define Z_MAXLIT     (40u * 1024u)   // literal bytes per sub-block (16 KiB of tiles + up to ~16 KiB carried + slack)
+#define Z_MAXLIT     (64u * 1024u + 256u)   // literal bytes per block: a pending match can hold back the sub-block flushes of a whole
+                                           // 64 KiB window (match, then incompressible data to the end), so the bound is the window
 #define Z_BITWORDS   3072u           // shared bit buffer: 12 KiB
 #define Z_HUF_MAXBITS 11
 #define Z_WARM        16u             // warm-up symbols of a speculative FSE chain chunk
