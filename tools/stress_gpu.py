@@ -3,7 +3,9 @@ usage: stress_gpu.py <seconds> [seed]
 Each round draws a data recipe (generator classes, random / repeated / zero spans glued at random places), a total
 size and a chunk size, then checks:
   LZ4 : GPU frames == oracle twin, byte for byte; GPU decode and the oracle decoder restore the input
-  zstd: GPU frames decode with the oracle's RFC 8878 decoder, with the real libzstd (when oracle/_ref is built) and on the GPU"""
+  zstd: GPU frames decode with the oracle's RFC 8878 decoder, with the real libzstd (when oracle/_ref is built) and on the GPU
+  API : every third round, {LZ4MT,ZSTDCB}_compressCCtx / _decompressDCtx through in-memory callbacks with a random thread count:
+        same bytes as the device path, round trip, and streams made by the real reference (random level) decode through our API"""
 import sys, os, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -55,5 +57,18 @@ while time.time() < t_end:
         rc, b2, _ = o.ref_decompress(o.CODEC_ZSTD, g, n, threads=2); assert rc == 0 and np.array_equal(b2, src), ("libzstd decode", n, chunk)
     zd = z.ZstdDeviceDecompressor(g); zout, zst = zd.run(torch.from_numpy(g).cuda() if g.size else torch.empty(1, dtype=torch.uint8, device="cuda")); torch.cuda.synchronize()
     assert zd.out_total == n and int(zst.abs().sum().item()) == 0 and np.array_equal(zout[:n].cpu().numpy(), src), ("zstd gpu decode", n, chunk)
+    # ---- callback API (host pipeline): same bytes as the device path, round trip, and reference-made streams
+    if n <= (24 << 20) and rounds % 3 == 0:
+        T = int(rng.integers(1, 9))
+        for codec, dev_bytes in ((z.CODEC_LZ4, f), (z.CODEC_ZSTD, g)):
+            rc, fr, _ = z.compress_mem(codec, src, threads=T, level=int(rng.integers(1, 4)), chunk=chunk)
+            assert rc == 0 and fr.size == dev_bytes.size and np.array_equal(fr, dev_bytes), ("api compress != device path", codec, n, chunk, T)
+            rc, bk, _ = z.decompress_mem(codec, fr, n + 16, threads=T)
+            assert rc == 0 and bk.size == n and np.array_equal(bk, src), ("api decompress", codec, n, chunk, T)
+            if o.have_ref() and n:
+                rc, rf, _ = o.ref_compress(codec, src, threads=int(rng.integers(1, 5)), level=int(rng.choice([1, 3, 9])), chunk=chunk)
+                assert rc == 0
+                rc, bk, _ = z.decompress_mem(codec, rf, n + 16, threads=T)
+                assert rc == 0 and bk.size == n and np.array_equal(bk, src), ("api decompress of reference stream", codec, n, chunk, T)
     rounds += 1; nbytes += n
 print("stress ok: %d rounds, %.1f MiB, seed %d" % (rounds, nbytes / 2**20, seed))
