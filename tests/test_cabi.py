@@ -6,6 +6,7 @@ import os
 import re
 import subprocess
 
+import numpy as np
 import pytest
 
 import zstdmt_b200 as z
@@ -86,3 +87,45 @@ def test_chunk_count_and_bounds():
     assert L.zmt_chunk_count(1, 1 << 20) == 1
     assert L.zmt_chunk_count((1 << 20) + 1, 1 << 20) == 2
     assert L.zmt_lz4c_out_bound(1, 1 << 20) >= 1048679   # LZ4F_compressFrameBound(1 MiB)+12 (Appendix A)
+
+
+@pytest.mark.parametrize("level", [1, 3, 19])
+@pytest.mark.parametrize("kind", [z.GEN_TEXT, z.GEN_MIX, z.GEN_RANDOM, z.GEN_ZEROS])
+def test_zstd_host_block_scan_on_reference_frames(level, kind):
+    """zmt_zstd_scan_frame_host is host logic (the reader thread runs it per frame): on frames made by the real
+    reference it must account for every byte of the frame, report the frame's content size and reject truncation /
+    trailing bytes.  No GPU involved."""
+    import _oracle as o
+    if not o.have_ref():
+        pytest.skip("oracle/_ref not built")
+    import ctypes
+    L = z.lib()
+    n = (1 << 20) + 12345
+    src = z.gen_stream(kind, n, 1 << 20)
+    rc, framed, st = o.ref_compress(o.CODEC_ZSTD, src, threads=2, level=level, chunk=1 << 19)
+    assert rc == 0
+    offs, sizes = z.scan_frames(framed)
+    assert len(offs) == 3
+    dsz = L.zmt_zstd_blk_desc_bytes()
+    total = 0
+    for i in range(len(offs)):
+        fr = np.ascontiguousarray(framed[int(offs[i]) + 12: int(offs[i]) + 12 + int(sizes[i])])
+        cap = fr.size // 3 + 16
+        blocks = np.zeros(cap * dsz, np.uint8)
+        nblk = ctypes.c_uint32(0); scr = ctypes.c_uint64(0); cs = ctypes.c_uint64(0); nsq = ctypes.c_uint32(0)
+        rc = L.zmt_zstd_scan_frame_host(fr.ctypes.data, fr.size, 0, i, blocks.ctypes.data, ctypes.byref(nblk), cap, ctypes.byref(scr), ctypes.byref(cs), ctypes.byref(nsq))
+        assert rc == 0 and nblk.value >= 1
+        total += cs.value
+        # descriptors: comp_off (u64) + comp_size (u32) lead every record; blocks tile the frame after its header
+        rec = blocks[: nblk.value * dsz].reshape(nblk.value, dsz)
+        comp_off = rec[:, :8].copy().view("<u8")[:, 0]; comp_size = rec[:, 8:12].copy().view("<u4")[:, 0]
+        assert (np.diff(comp_off.astype(np.int64)) > 0).all() and int(comp_off[-1]) + int(comp_size[-1]) <= fr.size
+        # truncated frame / trailing byte
+        nb2 = ctypes.c_uint32(0); s2 = ctypes.c_uint64(0)
+        rc = L.zmt_zstd_scan_frame_host(fr.ctypes.data, fr.size - 1, 0, i, blocks.ctypes.data, ctypes.byref(nb2), cap, ctypes.byref(s2), ctypes.byref(cs), ctypes.byref(nsq))
+        assert rc != 0
+        fr2 = np.concatenate([fr, np.zeros(1, np.uint8)])
+        nb2 = ctypes.c_uint32(0); s2 = ctypes.c_uint64(0)
+        rc = L.zmt_zstd_scan_frame_host(fr2.ctypes.data, fr2.size, 0, i, blocks.ctypes.data, ctypes.byref(nb2), cap, ctypes.byref(s2), ctypes.byref(cs), ctypes.byref(nsq))
+        assert rc != 0
+    assert total == n

@@ -111,3 +111,17 @@ def test_oracle_rejects_corruption():
     bad = f.copy(); bad[12 + 4 + 2 + 8] ^= 1        # header checksum byte
     assert o.orc_decode(o.CODEC_LZ4, bad, src.size)[0] == -4
     assert o.orc_decode(o.CODEC_LZ4, f[:-3], src.size)[0] == -1
+
+
+@pytest.mark.parametrize("chunk", [65536, 200000, 1 << 20])
+def test_b200_encoder_twin_length_field_corner_cases(chunk):
+    """The CPU twin of the GPU LZ4 encoder on the stream that exercises every length-field form (15 / 270 / 1290 ...
+    boundaries, 255-runs, block-ending literals): the real liblz4 behind the reference wrapper must restore it."""
+    from _data import long_runs_stream
+    src = long_runs_stream(1)
+    framed = o.orc_encode_lz4(src, chunk)
+    rc, back = o.orc_decode(o.CODEC_LZ4, framed, src.size)
+    assert rc == 0 and np.array_equal(back, src)
+    if o.have_ref():
+        rc, back, st = o.ref_decompress(o.CODEC_LZ4, framed, src.size, threads=2)
+        assert rc == 0 and np.array_equal(back, src)
