@@ -55,11 +55,13 @@ int      zmt_lz4_compress_device(const void* d_in, uint64_t in_bytes, uint32_t c
 
 /* d_in/in_bytes = the framed stream in HBM; d_frame_off[f] = offset of frame f's 12-byte header, d_frame_csize[f] =
  * its payload size; d_out_off[f..f+1] = where frame f's content goes and how much room it has;
- * max_blocks_per_frame = max over frames of ceil(room / 64 KiB) (warps launched per frame: frames with independent
- * blocks are decoded one warp per block); d_out_size[f] / d_status[f] receive decoded bytes and a ZMT_ST_* code. */
-size_t   zmt_lz4d_workspace_bytes(uint32_t nframes);
+ * nslots = sum over frames of max(1, ceil(room_f / 64 KiB)): the capacity of the block table (one warp per LZ4F block,
+ * two passes: token parse + literals, then match execution; frames with linked blocks — what liblz4 emits for the
+ * reference — decode block-parallel too, a block waits on the previous one only where a match reaches into it);
+ * d_out_size[f] / d_status[f] receive decoded bytes and a ZMT_ST_* code. */
+size_t   zmt_lz4d_workspace_bytes(uint32_t nframes, uint32_t nslots, uint64_t in_bytes);
 int      zmt_lz4_decompress_device(const void* d_in, uint64_t in_bytes, const uint64_t* d_frame_off, const uint32_t* d_frame_csize, uint32_t nframes,
-                                   uint32_t max_blocks_per_frame, void* d_out, const uint64_t* d_out_off, uint64_t* d_out_size,
+                                   uint32_t nslots, void* d_out, const uint64_t* d_out_off, uint64_t* d_out_size,
                                    uint32_t* d_status, void* d_work, void* stream);
 
 /* ---- Zstandard ----  same layout contract as the LZ4 entry points; frames are single-segment zstd frames
@@ -82,24 +84,19 @@ int      zmt_zstd_decompress_device(const void* d_in, const void* d_blocks, uint
                                     const uint64_t* d_expect, const uint32_t* d_frame_seq, uint32_t nframes, void* d_out,
                                     const uint64_t* d_out_off, uint64_t* d_out_size, uint32_t* d_status, void* d_work, void* stream);
 
+/* ---- multi-GPU: one LZ4MT_* / ZSTDCB_* call deals its batches round-robin over the devices named by the
+ * environment variable ZSTDMT_GPUS ("all" or "0,1,..."; default: the calling thread's current device) and re-serialises
+ * the frames on the host.  zmt_device_batches(dev) = batches submitted to that device since the library was loaded. */
+uint64_t zmt_device_batches(int dev);
+
 /* ---- per-kernel device timing (CUDA events on the launching stream) ----
  * zmt_prof_begin() arms it; every kernel launched by the entry points above is bracketed by two
  * events; zmt_prof_end() (after the caller synchronised the stream) sums them per kernel id. */
 enum { ZMT_K_LZ4_COMPRESS = 0, ZMT_K_XXH32, ZMT_K_LZ4_SIZES, ZMT_K_SCAN, ZMT_K_LZ4_PACK, ZMT_K_LZ4_DECODE, ZMT_K_XXH32_DEC,
-       ZMT_K_ZSTD_COMPRESS, ZMT_K_ZSTD_PACK, ZMT_K_ZSTD_DECODE, ZMT_K_COUNT };
+       ZMT_K_ZSTD_COMPRESS, ZMT_K_ZSTD_PACK, ZMT_K_ZSTD_DECODE, ZMT_K_LZ4_DEXEC, ZMT_K_COUNT };
+/* LZ4 decode: ZMT_K_LZ4_DECODE = pass A (token parse + literals), ZMT_K_LZ4_DEXEC = pass B (match execution) */
 void zmt_prof_begin(void);
 int  zmt_prof_end(double* ms, int* count, int max_ids);
-
-/* ---- synthetic inputs (csrc/datagen.c) ---- */
-void zmt_gen_chunk(int kind, uint64_t chunk_index, uint8_t* buf, size_t n);
-void zmt_gen_stream(int kind, uint64_t first, uint64_t stride, size_t chunk, uint8_t* buf, size_t total, int nthreads);
-
-/* ---- memory-to-memory drivers of the callback API (csrc/memio_glue.c) ----
- * stats[0..4] = bytes written, frames, Insize counter, Outsize counter, (reads<<32 | writes) */
-size_t zmt_lz4_compress_mem(int threads, int level, int chunk, const void* src, size_t n, void* dst, size_t cap, size_t* stats);
-size_t zmt_lz4_decompress_mem(int threads, int inputsize, const void* src, size_t n, void* dst, size_t cap, size_t* stats);
-size_t zmt_zstd_compress_mem(int threads, int level, int chunk, const void* src, size_t n, void* dst, size_t cap, size_t* stats);
-size_t zmt_zstd_decompress_mem(int threads, int inputsize, const void* src, size_t n, void* dst, size_t cap, size_t* stats);
 
 #ifdef __cplusplus
 }

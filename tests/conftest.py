@@ -17,5 +17,6 @@ def _native_libs():
     """Build the product .so and the oracle before any test (no-ops when up to date)."""
     from zstdmt_b200 import build as b
     b.build_product()
+    b.build_harness()
     if not os.path.exists(os.path.join(ROOT, "oracle", "liboracle.so")) or os.path.isdir("/root/reference"):
         b.build_oracle()

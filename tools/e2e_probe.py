@@ -8,7 +8,7 @@ threads = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 chunk = 1 << 20; n = int(gib * (1 << 30))
 torch.cuda.set_device(0)
 src = z.gen_stream(z.GEN_MIX, n, chunk)
-L = z.lib(); cap = z.mt_bound(n, chunk); out = np.empty(cap, np.uint8); st = (ctypes.c_size_t * 5)()
+L = z.memio_lib(); cap = z.mt_bound(n, chunk); out = np.empty(cap, np.uint8); st = (ctypes.c_size_t * 5)()
 for it in range(3):
     t = time.perf_counter(); rc = L.zmt_lz4_compress_mem(threads, 1, chunk, src.ctypes.data, n, out.ctypes.data, cap, st); dt = time.perf_counter() - t
     print("compress e2e it%d rc=%d %.3fs  in %.2f GB/s  in+out %.2f GB/s" % (it, rc, dt, n / dt / 1e9, (n + st[0]) / dt / 1e9), flush=True)

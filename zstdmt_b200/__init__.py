@@ -24,7 +24,12 @@ GEN_ZEROS, GEN_TEXT, GEN_MIX, GEN_RANDOM = 0, 1, 2, 3
 ST_NAMES = {0: "ok", 1: "truncated", 2: "bad_magic", 3: "bad_header", 4: "hdr_checksum", 5: "block", 6: "dst_small",
             7: "content_checksum", 8: "content_size", 9: "trailing", 10: "unsupported", 11: "cuda", 12: "bad_arg"}
 
+GEN_LIB_PATH = os.path.join(_HERE, "libzmt_datagen.so")
+MEMIO_LIB_PATH = os.path.join(_HERE, "libzmt_memio.so")
+
 _lib = None
+_gen = None
+_memio = None
 
 
 class Buffer(ctypes.Structure):
@@ -49,14 +54,6 @@ def lib():
         from . import build as _b
         _b.build_product()
     L = ctypes.CDLL(LIB_PATH)
-    for name in ("lz4_compress_mem", "zstd_compress_mem"):
-        f = getattr(L, "zmt_" + name); f.restype = c_sz
-        f.argtypes = [ctypes.c_int] * 3 + [c_vp, c_sz, c_vp, c_sz, ctypes.POINTER(c_sz)]
-    for name in ("lz4_decompress_mem", "zstd_decompress_mem"):
-        f = getattr(L, "zmt_" + name); f.restype = c_sz
-        f.argtypes = [ctypes.c_int] * 2 + [c_vp, c_sz, c_vp, c_sz, ctypes.POINTER(c_sz)]
-    L.zmt_gen_stream.restype = None
-    L.zmt_gen_stream.argtypes = [ctypes.c_int, c_u64, c_u64, c_sz, c_vp, c_sz, ctypes.c_int]
     L.zmt_chunk_count.restype = c_u32; L.zmt_chunk_count.argtypes = [c_u64, c_u32]
     L.zmt_lz4c_workspace_bytes.restype = c_sz; L.zmt_lz4c_workspace_bytes.argtypes = [c_u32, c_u32]
     L.zmt_lz4c_out_bound.restype = c_u64; L.zmt_lz4c_out_bound.argtypes = [c_u32, c_u32]
@@ -72,7 +69,7 @@ def lib():
     L.zmt_zstdd_workspace_bytes.restype = c_sz; L.zmt_zstdd_workspace_bytes.argtypes = [c_u32, c_u32, c_u64]
     L.zmt_zstd_decompress_device.restype = ctypes.c_int
     L.zmt_zstd_decompress_device.argtypes = [c_vp, c_vp, c_u32, c_vp, c_vp, c_vp, c_u32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
-    L.zmt_lz4d_workspace_bytes.restype = c_sz; L.zmt_lz4d_workspace_bytes.argtypes = [c_u32]
+    L.zmt_lz4d_workspace_bytes.restype = c_sz; L.zmt_lz4d_workspace_bytes.argtypes = [c_u32, c_u32, c_u64]
     L.zmt_lz4_decompress_device.restype = ctypes.c_int
     L.zmt_lz4_decompress_device.argtypes = [c_vp, c_u64, c_vp, c_vp, c_u32, c_u32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
     for pre, api in (("LZ4MT", "lz4"), ("ZSTDCB", "zstd"), ("ZSTDMT", "zstd")):
@@ -90,15 +87,48 @@ def lib():
     return L
 
 
+def gen_lib():
+    """libzmt_datagen.so: the synthetic input generator (harness, no dependency on the product library)."""
+    global _gen
+    if _gen is None:
+        if not os.path.exists(GEN_LIB_PATH):
+            from . import build as _b
+            _b.build_harness()
+        G = ctypes.CDLL(GEN_LIB_PATH)
+        G.zmt_gen_stream.restype = None
+        G.zmt_gen_stream.argtypes = [ctypes.c_int, c_u64, c_u64, c_sz, c_vp, c_sz, ctypes.c_int]
+        _gen = G
+    return _gen
+
+
+def memio_lib():
+    """libzmt_memio.so: in-memory fn_read / fn_write drivers of LZ4MT_* / ZSTDCB_* (harness; links the product library)."""
+    global _memio
+    if _memio is None:
+        lib()
+        if not os.path.exists(MEMIO_LIB_PATH):
+            from . import build as _b
+            _b.build_harness()
+        M = ctypes.CDLL(MEMIO_LIB_PATH)
+        for name in ("lz4_compress_mem", "zstd_compress_mem"):
+            f = getattr(M, "zmt_" + name); f.restype = c_sz
+            f.argtypes = [ctypes.c_int] * 3 + [c_vp, c_sz, c_vp, c_sz, ctypes.POINTER(c_sz)]
+        for name in ("lz4_decompress_mem", "zstd_decompress_mem"):
+            f = getattr(M, "zmt_" + name); f.restype = c_sz
+            f.argtypes = [ctypes.c_int] * 2 + [c_vp, c_sz, c_vp, c_sz, ctypes.POINTER(c_sz)]
+        _memio = M
+    return _memio
+
+
 # ------------------------------------------------------------------ synthetic inputs
 def gen_stream(kind, nbytes, chunk, first=0, stride=1, threads=None, out=None):
-    """Deterministic synthetic stream (csrc/datagen.c).  Returns a numpy uint8 array."""
+    """Deterministic synthetic stream (harness/datagen.c).  Returns a numpy uint8 array."""
     if out is None:
         out = np.empty(nbytes, dtype=np.uint8)
     if threads is None:
         threads = min(32, os.cpu_count() or 1)
     if nbytes:
-        lib().zmt_gen_stream(kind, first, stride, chunk, out.ctypes.data, nbytes, threads)
+        gen_lib().zmt_gen_stream(kind, first, stride, chunk, out.ctypes.data, nbytes, threads)
     return out
 
 
@@ -118,14 +148,14 @@ def mt_bound(n, chunk):
 
 
 def compress_mem(codec, data, threads=4, level=1, chunk=1 << 20):
-    """{LZ4MT,ZSTDCB}_compressCCtx through in-memory callbacks (csrc/memio_glue.c)."""
-    L = lib()
+    """{LZ4MT,ZSTDCB}_compressCCtx through in-memory callbacks (harness/memio_glue.c)."""
+    L = memio_lib()
     fn = L.zmt_lz4_compress_mem if codec == CODEC_LZ4 else L.zmt_zstd_compress_mem
     return _mem_call(fn, (threads, level, chunk), data, mt_bound(len(data), chunk))
 
 
 def decompress_mem(codec, data, out_cap, threads=4, inputsize=0):
-    L = lib()
+    L = memio_lib()
     fn = L.zmt_lz4_decompress_mem if codec == CODEC_LZ4 else L.zmt_zstd_decompress_mem
     return _mem_call(fn, (threads, inputsize), data, out_cap)
 
@@ -204,18 +234,20 @@ class Lz4DeviceDecompressor:
         self.d_cs = torch.from_numpy(np.asarray(frame_csize, dtype=np.int32)).to(device)
         oo = np.zeros(self.n + 1, dtype=np.int64); oo[1:] = np.cumsum(np.asarray(out_sizes, dtype=np.int64))
         self.out_total = int(oo[-1])
-        self.max_bpf = int(max(1, max((int(x) + 65535) // 65536 for x in out_sizes))) if len(out_sizes) else 1
+        osz = np.asarray(out_sizes, dtype=np.int64)
+        self.nslots = int(np.maximum(1, (osz + 65535) // 65536).sum()) if len(osz) else 1
         self.d_out_off = torch.from_numpy(oo).to(device)
         self.out = torch.empty(max(self.out_total, 1), dtype=torch.uint8, device=device)
         self.out_size = torch.zeros(self.n, dtype=torch.int64, device=device)
         self.status = torch.zeros(self.n, dtype=torch.int32, device=device)
-        self.work = torch.empty(L.zmt_lz4d_workspace_bytes(self.n), dtype=torch.uint8, device=device)
+        self.in_bytes_cap = int((np.asarray(frame_off, dtype=np.int64) + 12 + np.asarray(frame_csize, dtype=np.int64)).max()) if self.n else 0
+        self.work = torch.empty(L.zmt_lz4d_workspace_bytes(self.n, self.nslots, self.in_bytes_cap), dtype=torch.uint8, device=device)
 
     def run(self, d_framed, stream=None):
         torch = _torch()
         s = stream if stream is not None else torch.cuda.current_stream()
         rc = lib().zmt_lz4_decompress_device(d_framed.data_ptr(), d_framed.numel(), self.d_off.data_ptr(), self.d_cs.data_ptr(), self.n,
-                                             self.max_bpf, self.out.data_ptr(), self.d_out_off.data_ptr(), self.out_size.data_ptr(),
+                                             self.nslots, self.out.data_ptr(), self.d_out_off.data_ptr(), self.out_size.data_ptr(),
                                              self.status.data_ptr(), self.work.data_ptr(), s.cuda_stream)
         if rc != 0:
             raise RuntimeError("zmt_lz4_decompress_device failed: %s" % ST_NAMES.get(rc, rc))

@@ -1,6 +1,8 @@
 """Build the in-tree native libraries (no torch extension machinery, plain nvcc / gcc).
 
   zstdmt_b200/libzstdmt_b200.so   CUDA kernels (sm_100a) + host pipeline + C-ABI   [the product]
+  zstdmt_b200/libzmt_datagen.so   synthetic input generator (harness/datagen.c)     [bench / test harness, no dependencies]
+  zstdmt_b200/libzmt_memio.so     in-memory fn_read / fn_write drivers of the C-ABI [bench / test harness, links the product]
   oracle/liboracle.so             CPU restatement                                  [test infrastructure]
   oracle/_ref/libzstdmt_ref.so    unmodified reference wrapper, only when /root/reference exists
 """
@@ -12,10 +14,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libzstdmt_b200.so")
+HSRC = os.path.join(HERE, "harness")
+LIB_GEN = os.path.join(HERE, "libzmt_datagen.so")
+LIB_MEMIO = os.path.join(HERE, "libzmt_memio.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC,-O3,-pthread", "-DGLUE_PREFIX=zmt_", "-shared",
+    "-Xcompiler", "-fPIC,-O3,-pthread", "-shared",
 ]
 
 
@@ -51,6 +56,20 @@ def build_product(force=False, verbose=False):
     return LIB
 
 
+def build_harness(force=False):
+    """The two harness libraries (plain gcc).  libzmt_memio.so resolves LZ4MT_* / ZSTDCB_* from the product library."""
+    gen_src, io_src = os.path.join(HSRC, "datagen.c"), os.path.join(HSRC, "memio_glue.c")
+    if force or _stale(LIB_GEN, [gen_src]):
+        r = subprocess.run(["gcc", "-O3", "-fPIC", "-pthread", "-shared", "-o", LIB_GEN, gen_src, "-lpthread"], cwd=ROOT, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr); raise RuntimeError("gcc failed building libzmt_datagen.so")
+    if force or _stale(LIB_MEMIO, [io_src, LIB]):
+        r = subprocess.run(["gcc", "-O3", "-fPIC", "-shared", "-DGLUE_PREFIX=zmt_", "-o", LIB_MEMIO, io_src, "-L" + HERE, "-l:libzstdmt_b200.so",
+                            "-Wl,-rpath,$ORIGIN"], cwd=ROOT, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr); raise RuntimeError("gcc failed building libzmt_memio.so")
+
+
 def build_oracle():
     r = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], capture_output=True, text=True)
     if r.returncode != 0:
@@ -65,6 +84,7 @@ def build_cli():
 
 def build_all(force=False, verbose=False):
     build_product(force=force, verbose=verbose)
+    build_harness(force=force)
     build_oracle()
     build_cli()
 

@@ -15,7 +15,11 @@
 // Callback contract kept: reads never overlap reads, writes never overlap writes, a read and a
 // write may overlap (as with the reference's read_mutex / write_mutex).  No CPU codec fallback:
 // if the CUDA runtime or a kernel fails the call returns *_error_compression_library.
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE
+#endif
 #include <cuda_runtime.h>
+#include <sched.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -102,6 +106,76 @@ std::vector<int> env_devices()
     return devs;
 }
 
+// batches submitted per device since the library was loaded (zmt_device_batches: lets a caller / test see the round-robin deal)
+std::atomic<uint64_t> g_dev_batches[64];
+
+// ------------------------------------------------------------------ NUMA placement
+// The staging rings are the memcpy targets / sources of the (serialised) fn_read / fn_write callbacks and the DMA
+// sources / targets of the GPU: both want them on the GPU's own NUMA node.  Linux places pages on the node of the
+// thread that first touches them, so the pinned buffers are allocated with the calling thread temporarily bound to
+// the CPUs of the GPU's PCIe root (/sys/bus/pci/devices/<id>/local_cpulist), and the reader / writer threads of a
+// call run there too.  ZSTDMT_B200_NUMA=0 turns both off.
+struct CpuSet { cpu_set_t set; bool ok = false; };
+
+bool numa_enabled() { static int on = -1; if (on < 0) { const char* v = getenv("ZSTDMT_B200_NUMA"); on = (v && *v == '0') ? 0 : 1; } return on == 1; }
+
+CpuSet device_local_cpus(int dev)
+{
+    CpuSet r; CPU_ZERO(&r.set);
+    if (!numa_enabled()) return r;
+    char id[32] = {0};
+    if (cudaDeviceGetPCIBusId(id, (int)sizeof(id), dev) != cudaSuccess) { cudaGetLastError(); return r; }
+    for (char* q = id; *q; q++) if (*q >= 'A' && *q <= 'Z') *q = (char)(*q - 'A' + 'a');
+    char path[128]; snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/local_cpulist", id);
+    FILE* f = fopen(path, "r");
+    if (!f) return r;
+    char buf[1024] = {0};
+    const bool got = fgets(buf, sizeof(buf), f) != nullptr;
+    fclose(f);
+    if (!got) return r;
+    int n = 0;
+    for (const char* q = buf; *q && *q != '\n';) {          // "0-31,64-95"
+        char* end = nullptr; long a = strtol(q, &end, 10); if (end == q) break;
+        long b = a; q = end;
+        if (*q == '-') { b = strtol(q + 1, &end, 10); if (end == q + 1) break; q = end; }
+        for (long c = a; c <= b && c < CPU_SETSIZE; c++) { if (c >= 0) { CPU_SET((int)c, &r.set); n++; } }
+        if (*q == ',') q++;
+    }
+    // stay inside the affinity the process was given (containers, numactl)
+    cpu_set_t cur; CPU_ZERO(&cur);
+    if (sched_getaffinity(0, sizeof(cur), &cur) == 0) {
+        cpu_set_t both; CPU_AND(&both, &cur, &r.set);
+        if (CPU_COUNT(&both) == 0) return r;
+        r.set = both;
+    }
+    r.ok = n > 0;
+    return r;
+}
+
+// binds the calling thread for the lifetime of the object (or for good with keep())
+struct ScopedAffinity {
+    cpu_set_t old; bool active = false;
+    explicit ScopedAffinity(const CpuSet& c) {
+        if (!c.ok) return;
+        CPU_ZERO(&old);
+        if (sched_getaffinity(0, sizeof(old), &old) != 0) return;
+        active = sched_setaffinity(0, sizeof(c.set), &c.set) == 0;
+    }
+    ~ScopedAffinity() { if (active) sched_setaffinity(0, sizeof(old), &old); }
+};
+
+// all devices of a call on one node -> that node's CPUs, else nothing (the staging rings then live on several nodes)
+CpuSet common_local_cpus(const std::vector<int>& devs)
+{
+    CpuSet r; CPU_ZERO(&r.set);
+    for (size_t i = 0; i < devs.size(); i++) {
+        const CpuSet c = device_local_cpus(devs[i]);
+        if (!c.ok) return CpuSet();
+        if (i == 0) r = c; else if (!CPU_EQUAL(&r.set, &c.set)) return CpuSet();
+    }
+    return r;
+}
+
 // ------------------------------------------------------------------ optional stage timing (ZSTDMT_B200_TRACE=1)
 struct StageClock {
     double cb = 0, wait = 0, gpu = 0;       // seconds: inside callbacks / waiting for a slot or queue / CUDA sync + copies
@@ -135,7 +209,8 @@ struct Slot {
     uint8_t *h_tab = nullptr, *d_tab = nullptr; size_t tab_bytes = 0;
     // batch contents
     uint32_t n = 0;              // chunks / frames in this batch
-    uint32_t max_bpf = 1;        // decompress: max 64 KiB blocks per frame in this batch
+    uint32_t nslots = 1;         // lz4 decompress: block-table slots of this batch (sum over frames of max(1, ceil(out / 64 KiB)))
+    uint64_t scr_cap = 0;        // zstd decompress: entropy scratch bytes the workspace was sized for
     // zstd decompress: block descriptors built by the reader (pinned) + device copy, scratch demand of the batch
     uint8_t *h_blk = nullptr, *d_blk = nullptr; uint32_t blk_cap = 0, nblk = 0; uint64_t scratch_used = 0;
     size_t in_used = 0, out_used = 0;
@@ -151,6 +226,9 @@ inline Tables tables_at(uint8_t* base, size_t cap)
     Tables t; t.a = (uint64_t*)base; t.b = t.a + cap + 1; t.c = t.b + cap + 1; t.f = t.c + cap + 1;
     t.d = (uint32_t*)(t.f + cap + 1); t.e = t.d + cap; t.g = t.e + cap; return t;
 }
+
+// lz4 decode block table capacity of a slot: every frame owns max(1, ceil(out / 64 KiB)) slots
+inline uint32_t lz4_slot_cap(size_t out_cap, size_t tab_cap) { return (uint32_t)(out_cap / 65536 + tab_cap + 1); }
 
 void slot_free_raw(Slot& s)
 {
@@ -174,6 +252,7 @@ bool slot_alloc_raw(Slot& s, int dev, size_t in_cap, size_t out_cap, size_t work
 {
     s.dev = dev;
     if (cudaSetDevice(dev) != cudaSuccess) return false;
+    const ScopedAffinity bind(device_local_cpus(dev));     // first touch of the pinned rings happens on the GPU's node
     bool ok = true;
     ok = ok && cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming) == cudaSuccess;
@@ -291,7 +370,9 @@ size_t compress_run(Ctx* c, GenRdWr* rw)
 
     // ---- reader: fills slots in sequence order (pt_compress read section, lz4-mt_compress.c:255-277)
     StageClock ck_r, ck_w, ck_s;
+    const CpuSet host_cpus = common_local_cpus(c->devs);
     std::thread reader([&]() {
+        const ScopedAffinity bind(host_cpus);
         size_t frames_read = 0; bool eof = false;
         while (!eof) {
             Slot* s;
@@ -330,6 +411,7 @@ size_t compress_run(Ctx* c, GenRdWr* rw)
 
     // ---- writer: in-order emission (pt_write, lz4-mt_compress.c:178-205)
     std::thread writer([&]() {
+        const ScopedAffinity bind(host_cpus);
         for (;;) {
             Slot* s;
             {
@@ -387,6 +469,7 @@ size_t compress_run(Ctx* c, GenRdWr* rw)
         if (ce == cudaSuccess) ce = cudaMemcpyAsync(Td.d, Th.d, (size_t)s->n * 4, cudaMemcpyHostToDevice, s->stream);
         int st = ZMT_ST_CUDA;
         if (ce == cudaSuccess) st = ops->compress(s->d_in, 0, (uint32_t)chunk, Td.d, s->n, s->d_work, s->d_out, Td.a, s->stream);
+        if (s->dev >= 0 && s->dev < 64) g_dev_batches[s->dev]++;
         if (st == ZMT_ST_OK) {
             ce = cudaMemcpyAsync(Th.a, Td.a, ((size_t)s->n + 1) * 8, cudaMemcpyDeviceToHost, s->stream);
             if (ce == cudaSuccess) ce = cudaEventRecord(s->ev, s->stream);
@@ -409,12 +492,18 @@ size_t compress_run(Ctx* c, GenRdWr* rw)
 // Output size of one payload, from its own header (pt_decompress sizes the buffer from
 // LE64 @ payload+6, lz4-mt_decompress.c:329-335; zstd: frame content size).
 // Returns false if the header is unusable.
-bool lz4f_out_size(const uint8_t* p, size_t n, size_t frame_idx, uint64_t* out)
+bool lz4f_out_size(const uint8_t* p, size_t n, uint64_t* out)
 {
     if (n < 7 || rd32(p) != LZ4F_MAGIC) { *out = 0; return true; }     // the device decoder reports the precise status
     const uint32_t flg = p[4], bd = p[5];
-    if (flg & 0x08) { if (n < 15) return false; *out = rd64(p + 6); return true; }
-    (void)frame_idx;
+    if (flg & 0x08) {
+        if (n < 15) return false;
+        // untrusted field: LZ4 cannot expand by more than 255x, anything larger is a corrupt header (the reference
+        // fails its malloc there); without this bound a huge value would wrap the running output offsets
+        const uint64_t v = rd64(p + 6);
+        if (v > (uint64_t)n * 255 + 65536) return false;
+        *out = v; return true;
+    }
     // no content-size field: bound it by walking the block headers (each block <= blockMaxSize)
     const uint32_t id = (bd >> 4) & 7; if (id < 4) return false;
     const uint64_t blkmax = 1ull << (8 + 2 * id);
@@ -424,7 +513,7 @@ bool lz4f_out_size(const uint8_t* p, size_t n, size_t frame_idx, uint64_t* out)
         if (bh == 0) break;
         const uint32_t bs = bh & 0x7FFFFFFFu;
         total += (bh & 0x80000000u) ? bs : blkmax;
-        pos += bs + ((flg & 0x10) ? 4 : 0);
+        pos += (size_t)bs + ((flg & 0x10) ? 4 : 0);
     }
     *out = total; return true;
 }
@@ -477,7 +566,7 @@ size_t decompress_single_stream(Ctx* c, GenRdWr* rw, const uint8_t* first, size_
     c->insize = n;                                          // every byte of the stream, sniffed bytes included
     // ---- host scan: frame table (+ zstd block table)
     std::vector<uint64_t> foff, ooff(1, 0), expect; std::vector<uint32_t> fcs, first_blk(1, 0), fseq;
-    std::vector<uint8_t> blocks; uint32_t nblk = 0; uint64_t scratch = 0; uint32_t max_bpf = 1;
+    std::vector<uint8_t> blocks; uint32_t nblk = 0; uint64_t scratch = 0; uint64_t nslots = 0;
     const size_t dsz = zmt_zstd_blk_desc_bytes();
     if (is_zstd) blocks.resize((n / 3 + 16) * dsz);
     size_t pos = 0;
@@ -507,7 +596,7 @@ size_t decompress_single_stream(Ctx* c, GenRdWr* rw, const uint8_t* first, size_
             if (q > n) { c->lib_errcode = ZMT_ST_TRUNCATED; return E.frame_decompress; }
             const uint64_t osz = (flg & 8) ? rd64(s + pos + 6) : bound;
             foff.push_back(pos); fcs.push_back((uint32_t)(q - pos)); ooff.push_back(ooff.back() + osz);
-            const uint64_t nb = (osz + 65535) / 65536; if (nb > max_bpf) max_bpf = (uint32_t)(nb > 0xFFFFFFu ? 0xFFFFFFu : nb);
+            { const uint64_t nb = (osz + 65535) / 65536; nslots += nb ? nb : 1; }
             pos = q;
         } else {
             if (magic < 0xFD2FB522u || magic > 0xFD2FB528u) return E.data_error;
@@ -530,7 +619,7 @@ size_t decompress_single_stream(Ctx* c, GenRdWr* rw, const uint8_t* first, size_
     Tables T = tables_at(h_tab.data(), nf);
     for (uint32_t i = 0; i < nf; i++) { T.a[i] = foff[i]; T.b[i] = ooff[i]; if (is_zstd) { T.f[i] = expect[i]; T.d[i] = fseq[i]; T.g[i] = first_blk[i]; } else T.d[i] = fcs[i]; }
     T.b[nf] = total; if (is_zstd) T.g[nf] = nblk;
-    const size_t wk = is_zstd ? zmt_zstdd_workspace_bytes(nf, nblk, scratch) : zmt_lz4d_workspace_bytes(nf);
+    const size_t wk = is_zstd ? zmt_zstdd_workspace_bytes(nf, nblk, scratch) : zmt_lz4d_workspace_bytes(nf, (uint32_t)nslots, in.size());
     if (!d_in.alloc(in.size() + 256) || !d_out.alloc(total + 256) || !d_tab.alloc(tab_bytes) || !d_work.alloc(wk) || (is_zstd && !d_blk.alloc((size_t)nblk * dsz))) { cudaGetLastError(); return E.mem; }
     cudaStream_t st = nullptr;
     if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { c->lib_errcode = ZMT_ST_CUDA; return E.library; }
@@ -539,7 +628,7 @@ size_t decompress_single_stream(Ctx* c, GenRdWr* rw, const uint8_t* first, size_
     cudaMemcpyAsync(d_tab.p, h_tab.data(), tab_bytes, cudaMemcpyHostToDevice, st);
     if (is_zstd && nblk) cudaMemcpyAsync(d_blk.p, blocks.data(), (size_t)nblk * dsz, cudaMemcpyHostToDevice, st);
     const int rc = is_zstd ? zmt_zstd_decompress_device(d_in.p, d_blk.p, nblk, Td.g, Td.f, Td.d, nf, d_out.p, Td.b, Td.c, Td.e, d_work.p, st)
-                           : zmt_lz4_decompress_device(d_in.p, in.size(), Td.a, Td.d, nf, max_bpf, d_out.p, Td.b, Td.c, Td.e, d_work.p, st);
+                           : zmt_lz4_decompress_device(d_in.p, in.size(), Td.a, Td.d, nf, (uint32_t)nslots, d_out.p, Td.b, Td.c, Td.e, d_work.p, st);
     std::vector<uint8_t> out(total ? total : 1);
     std::vector<uint32_t> status(nf); std::vector<uint64_t> osz(nf);
     cudaError_t ce = cudaSuccess;
@@ -619,8 +708,9 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
         for (size_t i = 0; i < P.slots.size(); i++)
         {
             // zstd scratch: 16 B per sequence + the literals: ~2x the output on text, bounded at 3x + tables (the reader closes a batch early otherwise)
-            const size_t wk = is_zstd ? zmt_zstdd_workspace_bytes((uint32_t)tab_cap, kBlkCap, 3 * (uint64_t)out_cap0) : zmt_lz4d_workspace_bytes((uint32_t)tab_cap);
+            const size_t wk = is_zstd ? zmt_zstdd_workspace_bytes((uint32_t)tab_cap, kBlkCap, 3 * (uint64_t)out_cap0) : zmt_lz4d_workspace_bytes((uint32_t)tab_cap, lz4_slot_cap(out_cap0, tab_cap), in_cap0);
             if (!slot_alloc(P.slots[i], c->devs[i % c->devs.size()], in_cap0, out_cap0, wk, tab_cap) || (is_zstd && !slot_ensure_blocks(P.slots[i], kBlkCap))) { ctx_release_slots(c); return E.mem; }
+            P.slots[i].scr_cap = is_zstd ? 3 * (uint64_t)P.slots[i].out_cap : 0;
         }
     }
     const size_t N = P.slots.size();
@@ -630,7 +720,9 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
     StageClock rd_clk, wr_clk; double rd_scan = 0, rd_total = 0, wr_total = 0;     // ZSTDMT_B200_TRACE=1
     const bool tr = trace_on();
     // ---- reader (pt_read, lz4-mt_decompress.c:192-281 / zstd-mt_decompress.c:209-369)
+    const CpuSet host_cpus = common_local_cpus(c->devs);
     std::thread reader([&]() {
+        const ScopedAffinity bind(host_cpus);
         const double t_start = tr ? StageClock::now() : 0;
         bool eof = false;
         std::vector<uint8_t> carry;              // a frame that did not fit the previous slot
@@ -649,31 +741,60 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
             uint32_t n = 0; size_t in_used = 0; uint64_t out_used = 0; size_t stat_in = 0;
             bool failed = false;
             uint32_t nblk = 0; uint64_t scr = 0;                 // zstd: block descriptors + scratch demand of this batch
-            const uint64_t scr_cap = is_zstd ? 3 * (uint64_t)s->out_cap : 0;
-            auto grow = [&](size_t need_in, uint64_t need_out) -> bool {   // empty slot too small for one frame: reallocate it
-                if (need_in <= s->in_cap && need_out <= s->out_cap) return true;
-                const int dev = s->dev; const size_t nin = need_in > s->in_cap ? need_in : s->in_cap, nout = need_out > s->out_cap ? (size_t)need_out : s->out_cap;
+            // (re)allocate the still empty slot so that one frame of these dimensions fits; takes P.mu for the swap because the
+            // writer's wait predicate reads s->state
+            auto grow = [&](size_t need_in, uint64_t need_out, uint64_t need_scr, uint32_t need_blk) -> bool {
+                if (need_in <= s->in_cap && need_out <= s->out_cap && need_scr <= s->scr_cap && need_blk <= s->blk_cap) return true;
+                const int dev = s->dev;
+                const size_t nin = need_in > s->in_cap ? need_in : s->in_cap, nout = need_out > s->out_cap ? (size_t)need_out : s->out_cap;
+                const uint64_t nscr = is_zstd ? (need_scr > 3 * (uint64_t)nout ? need_scr : 3 * (uint64_t)nout) : 0;
+                const uint32_t nb = need_blk > s->blk_cap ? need_blk : s->blk_cap;
                 const size_t tc = s->tab_cap;
-                const size_t wk = is_zstd ? zmt_zstdd_workspace_bytes((uint32_t)tc, kBlkCap, 3 * (uint64_t)nout) : s->work_cap;
+                const size_t wk = is_zstd ? zmt_zstdd_workspace_bytes((uint32_t)tc, nb, nscr) : zmt_lz4d_workspace_bytes((uint32_t)tc, lz4_slot_cap(nout, tc), nin);
+                std::lock_guard<std::mutex> g(P.mu);
                 slot_free(*s);
-                return slot_alloc(*s, dev, nin, nout, wk, tc) && (!is_zstd || slot_ensure_blocks(*s, kBlkCap));
+                if (!slot_alloc(*s, dev, nin, nout, wk, tc) || (is_zstd && !slot_ensure_blocks(*s, nb))) return false;
+                s->scr_cap = nscr;
+                return true;
+            };
+            // Put one whole frame (12-byte header + payload, held in `fr`) at the start of the empty slot, growing the slot
+            // (input, output, zstd block table and entropy scratch) until it fits.  Returns false after P.fail().
+            auto place_first = [&](const std::vector<uint8_t>& fr) -> bool {
+                const size_t toRead = fr.size() - 12;
+                if (!grow(fr.size(), 0, 0, 0)) { P.fail(E.mem); return false; }
+                uint64_t osz = 0; uint32_t nsq = 0;
+                if (!is_zstd) {
+                    if (!lz4f_out_size(fr.data() + 12, toRead, &osz)) { c->lib_errcode = ZMT_ST_BAD_HEADER; P.fail(E.library); return false; }
+                    if (!grow(fr.size(), osz, 0, 0)) { P.fail(E.mem); return false; }
+                    memcpy(s->h_in, fr.data(), fr.size());
+                } else {
+                    for (int tries = 0;; tries++) {
+                        memcpy(s->h_in, fr.data(), fr.size());
+                        uint64_t cs = 0; nblk = 0; scr = 0;
+                        const int zr = zmt_zstd_scan_frame_host(s->h_in + 12, toRead, 12, 0, s->h_blk, &nblk, s->blk_cap, &scr, &cs, &nsq);
+                        if (zr == ZMT_ST_DST_SMALL && tries < 2) {          // more blocks than descriptors: every block costs >= 3 bytes
+                            if (!grow(fr.size(), 0, 0, (uint32_t)(toRead / 3 + 16))) { P.fail(E.mem); return false; }
+                            continue;
+                        }
+                        if (zr != ZMT_ST_OK) { c->lib_errcode = (size_t)zr; P.fail(zr == ZMT_ST_TRUNCATED || zr == ZMT_ST_TRAILING ? E.frame_decompress : E.library); return false; }
+                        osz = cs;
+                        if (osz <= s->out_cap && scr <= s->scr_cap) break;
+                        if (tries >= 2 || !grow(fr.size(), osz, scr, 0)) { P.fail(E.mem); return false; }
+                    }
+                }
+                T = tables_at(s->h_tab, s->tab_cap);
+                T.a[0] = 0; T.d[0] = (uint32_t)toRead; T.b[0] = 0;
+                if (is_zstd) { T.g[0] = 0; T.f[0] = osz; T.d[0] = nsq; }
+                in_used = fr.size(); out_used = osz; n = 1;
+                return true;
             };
             if (!carry.empty()) {
-                if (!grow(carry.size(), carry_out)) { P.fail(E.mem); break; }
-                T = tables_at(s->h_tab, s->tab_cap);
-                memcpy(s->h_in, carry.data(), carry.size());
-                T.a[0] = 0; T.d[0] = (uint32_t)(carry.size() - 12); T.b[0] = 0;
-                if (is_zstd) {
-                    uint64_t cs = 0; uint32_t nsq = 0; T.g[0] = 0;
-                    int zr = zmt_zstd_scan_frame_host(s->h_in + 12, carry.size() - 12, 12, 0, s->h_blk, &nblk, s->blk_cap, &scr, &cs, &nsq);
-                    if (zr != ZMT_ST_OK) { c->lib_errcode = (size_t)zr; P.fail(E.library); break; }
-                    T.f[0] = cs; T.d[0] = nsq;
-                }
-                in_used = carry.size(); out_used = carry_out; n = 1; carry.clear();
+                if (!place_first(carry)) break;
+                carry.clear();
             }
             while (n < s->tab_cap) {
                 uint8_t hdr[12]; size_t pre = 0;
-                if (hdr_pending) { memcpy(hdr, first, 12); hdr_pending = false; pre = first_payload_have; if (c->codec == CODEC_LZ4) stat_in += 0; }
+                if (hdr_pending) { memcpy(hdr, first, 12); hdr_pending = false; pre = first_payload_have; }
                 else {
                     size_t g = 0; size_t e = read_some(E, rw, hdr, 12, &g);
                     if (e) { P.fail(e); failed = true; break; }
@@ -686,11 +807,11 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
                 if (c->codec == CODEC_LZ4) stat_in += 12;
                 const size_t toRead = rd32(hdr + 8);
                 if (toRead < pre) { P.fail(E.data_error); failed = true; break; }
-                // where to put it: current slot if it fits, else a temporary carry buffer
-                uint8_t* dstp; bool to_carry = false;
+                // where to put it: the current slot if it fits behind the frames already there, else a temporary buffer
+                // (first frame of a batch that needs a bigger slot, or a frame that moves to the next batch)
+                uint8_t* dstp; bool to_tmp = false;
                 if (in_used + 12 + toRead <= s->in_cap) dstp = s->h_in + in_used;
-                else if (n == 0) { if (!grow(12 + toRead, 0)) { P.fail(E.mem); failed = true; break; } T = tables_at(s->h_tab, s->tab_cap); dstp = s->h_in; }
-                else { carry.resize(12 + toRead); dstp = carry.data(); to_carry = true; }
+                else { carry.resize(12 + toRead); dstp = carry.data(); to_tmp = true; }
                 memcpy(dstp, hdr, 12);
                 if (pre) memcpy(dstp + 12, first + 12, pre);
                 const double tc0 = tr ? StageClock::now() : 0;
@@ -699,35 +820,35 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
                 if (e) { P.fail(e); failed = true; break; }
                 if (g != toRead - pre) { P.fail(E.data_error); failed = true; break; }
                 stat_in += g;
-                uint64_t osz = 0; bool okh = c->codec == CODEC_LZ4 ? lz4f_out_size(dstp + 12, toRead, c->frames + n, &osz) : zstd_out_size(dstp + 12, toRead, &osz);
-                if (!okh) { c->lib_errcode = ZMT_ST_BAD_HEADER; P.fail(c->codec == CODEC_LZ4 ? E.library : E.library); failed = true; break; }
-                if (to_carry) { carry_out = osz; break; }
-                uint32_t nblk_new = nblk; uint64_t scr_new = scr; uint32_t nsq = 0;
-                if (is_zstd) {
-                    // block table of this frame (descriptors are appended; rolled back if the frame moves to the next batch)
+                if (to_tmp) {
+                    if (n > 0) break;                                   // next batch starts with it
+                    if (!place_first(carry)) { failed = true; break; }
+                    carry.clear();
+                    continue;
+                }
+                uint64_t osz = 0; uint32_t nsq = 0;
+                uint32_t nblk_new = nblk; uint64_t scr_new = scr;
+                bool moves = false;                                     // does not fit behind the others: first frame of the next batch
+                if (!is_zstd) {
+                    if (!lz4f_out_size(dstp + 12, toRead, &osz)) { c->lib_errcode = ZMT_ST_BAD_HEADER; P.fail(E.library); failed = true; break; }
+                } else {
+                    // block table of this frame (descriptors are appended; dropped again if the frame moves to the next batch)
                     uint64_t cs = 0;
                     const double ts0 = tr ? StageClock::now() : 0;
-                    int zr = zmt_zstd_scan_frame_host(dstp + 12, toRead, in_used + 12, n, s->h_blk, &nblk_new, s->blk_cap, &scr_new, &cs, &nsq);
+                    const int zr = zmt_zstd_scan_frame_host(dstp + 12, toRead, in_used + 12, n, s->h_blk, &nblk_new, s->blk_cap, &scr_new, &cs, &nsq);
                     if (tr) rd_scan += StageClock::now() - ts0;
-                    if (zr == ZMT_ST_DST_SMALL && n > 0) { carry.assign(dstp, dstp + 12 + toRead); carry_out = osz; break; }
-                    if (zr != ZMT_ST_OK) { c->lib_errcode = (size_t)zr; P.fail(zr == ZMT_ST_TRUNCATED || zr == ZMT_ST_TRAILING ? E.frame_decompress : E.library); failed = true; break; }
-                    if (scr_new > scr_cap && n > 0) { carry.assign(dstp, dstp + 12 + toRead); carry_out = osz; break; }
-                    if (scr_new > scr_cap) { c->lib_errcode = ZMT_ST_DST_SMALL; P.fail(E.library); failed = true; break; }
+                    if (zr == ZMT_ST_DST_SMALL) moves = true;
+                    else if (zr != ZMT_ST_OK) { c->lib_errcode = (size_t)zr; P.fail(zr == ZMT_ST_TRUNCATED || zr == ZMT_ST_TRAILING ? E.frame_decompress : E.library); failed = true; break; }
+                    else if (scr_new > s->scr_cap) moves = true;
                     osz = cs;
                 }
-                if (out_used + osz > s->out_cap) {
-                    if (n == 0) {
-                        // single frame larger than the slot: grow (payload already sits in h_in -> save it first)
-                        std::vector<uint8_t> save(dstp, dstp + 12 + toRead);
-                        if (!grow(12 + toRead, osz)) { P.fail(E.mem); failed = true; break; }
-                        T = tables_at(s->h_tab, s->tab_cap);
-                        memcpy(s->h_in, save.data(), save.size());
-                        if (is_zstd) {                     // the block table lived in the old slot: rebuild it
-                            uint64_t cs = 0; nblk_new = 0; scr_new = 0;
-                            int zr = zmt_zstd_scan_frame_host(s->h_in + 12, toRead, 12, 0, s->h_blk, &nblk_new, s->blk_cap, &scr_new, &cs, &nsq);
-                            if (zr != ZMT_ST_OK) { c->lib_errcode = (size_t)zr; P.fail(E.library); failed = true; break; }
-                        }
-                    } else { carry.assign(dstp, dstp + 12 + toRead); carry_out = osz; break; }
+                if (!moves && osz > s->out_cap - out_used) moves = true;
+                if (moves) {
+                    carry.assign(dstp, dstp + 12 + toRead);
+                    if (n > 0) break;
+                    if (!place_first(carry)) { failed = true; break; }  // a single frame larger than the slot: grow the slot
+                    carry.clear();
+                    continue;
                 }
                 T.a[n] = in_used; T.d[n] = (uint32_t)toRead; T.b[n] = out_used;
                 if (is_zstd) { T.g[n] = nblk; T.f[n] = osz; T.d[n] = nsq; nblk = nblk_new; scr = scr_new; }     // T.d doubles as the per-frame "needs sequential pass" flag
@@ -738,7 +859,7 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
             T.b[n] = out_used;
             if (is_zstd) { T.g[n] = nblk; s->nblk = nblk; s->scratch_used = scr; }
             s->n = n; s->in_used = in_used; s->out_used = (size_t)out_used;
-            { uint64_t mx = 1; for (uint32_t i = 0; i < n; i++) { const uint64_t o = T.b[i + 1] - T.b[i]; const uint64_t nb = (o + 65535) / 65536; if (nb > mx) mx = nb; } s->max_bpf = (uint32_t)mx; }
+            { uint64_t ns = 0; for (uint32_t i = 0; i < n; i++) { const uint64_t nb = (T.b[i + 1] - T.b[i] + 65535) / 65536; ns += nb ? nb : 1; } s->nslots = (uint32_t)ns; }
             {
                 std::lock_guard<std::mutex> g(P.mu);
                 c->insize += stat_in; c->frames += n;
@@ -753,6 +874,7 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
 
     // ---- writer (pt_write, lz4-mt_decompress.c:165-187)
     std::thread writer([&]() {
+        const ScopedAffinity bind(host_cpus);
         const double t_start = tr ? StageClock::now() : 0;
         for (;;) {
             Slot* s;
@@ -806,7 +928,8 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
         int st = ZMT_ST_CUDA;
         if (ce == cudaSuccess && is_zstd && s->nblk) ce = cudaMemcpyAsync(s->d_blk, s->h_blk, (size_t)s->nblk * zmt_zstd_blk_desc_bytes(), cudaMemcpyHostToDevice, s->stream);
         if (ce == cudaSuccess) st = is_zstd ? zmt_zstd_decompress_device(s->d_in, s->d_blk, s->nblk, Td.g, Td.f, Td.d, s->n, s->d_out, Td.b, Td.c, Td.e, s->d_work, s->stream)
-                                            : zmt_lz4_decompress_device(s->d_in, s->in_used, Td.a, Td.d, s->n, s->max_bpf, s->d_out, Td.b, Td.c, Td.e, s->d_work, s->stream);
+                                            : zmt_lz4_decompress_device(s->d_in, s->in_used, Td.a, Td.d, s->n, s->nslots, s->d_out, Td.b, Td.c, Td.e, s->d_work, s->stream);
+        if (s->dev >= 0 && s->dev < 64) g_dev_batches[s->dev]++;
         if (st == ZMT_ST_OK) {
             if (s->out_used) ce = cudaMemcpyAsync(s->h_out, s->d_out, s->out_used, cudaMemcpyDeviceToHost, s->stream);
             if (ce == cudaSuccess) ce = cudaMemcpyAsync(Th.c, Td.c, (size_t)s->n * 8, cudaMemcpyDeviceToHost, s->stream);
@@ -880,6 +1003,8 @@ const char* error_string(bool lz4, size_t code, size_t lib_errcode)
 
 // =================================================================== exported C ABI
 extern "C" {
+
+uint64_t zmt_device_batches(int dev) { return (dev >= 0 && dev < 64) ? g_dev_batches[dev].load() : 0; }
 
 size_t lz4mt_errcode = 0;      // lib/lz4-mt_common.c:16
 size_t zstdmt_errcode = 0;     // lib/zstd-mt_common.c:19

@@ -23,6 +23,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 #include <vector>
 #include "common.cuh"
 #include "zmt_dev.h"
@@ -701,216 +702,7 @@ lz4_frame_pack_kernel(const uint8_t* __restrict__ in, uint64_t in_bytes, uint32_
 }
 
 // ============================================================================ decoder
-// Work unit = one warp.  Frames with independent blocks (FLG.indep, what our encoder emits) get one warp per
-// 64 KiB block; frames with linked blocks (what liblz4 emits for the reference, lz4-mt_compress.c:141-146)
-// are decoded block after block by the frame's first warp, because a block may copy from the previous one.
-// The warp parses the sequence stream in lockstep (uniform control flow) out of a 1 KiB shared-memory window
-// that all 32 lanes refill with 16-byte loads, and spreads every literal / match copy over its lanes.
-#define D_WARPS 8
-#define D_WIN   1024u
-
-struct DWin { uint8_t* w; const uint8_t* gsrc; const uint8_t* in_end; int32_t pos; };   // pos: block-relative offset of w[0]
-
-__device__ __forceinline__ void dwin_fill(DWin& W, uint32_t ip, uint32_t lane)
-{
-    const int32_t np = (int32_t)ip - (int32_t)((uintptr_t)(W.gsrc + ip) & 15);
-    __syncwarp();
-#pragma unroll
-    for (uint32_t k = 0; k < D_WIN / 512; k++) {
-        const uint8_t* a = W.gsrc + np + (int32_t)(16 * (lane + 32 * k));
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (a + 16 <= W.in_end) v = *reinterpret_cast<const uint4*>(a);
-        else { uint8_t* b = reinterpret_cast<uint8_t*>(&v); for (int i = 0; i < 16; i++) if (a + i < W.in_end) b[i] = a[i]; }
-        reinterpret_cast<uint4*>(W.w)[lane + 32 * k] = v;
-    }
-    W.pos = np;
-    __syncwarp();
-}
-// make bytes [ip, ip + k) of the block available in the window (k <= D_WIN - 16)
-__device__ __forceinline__ void dwin_need(DWin& W, uint32_t ip, uint32_t k, uint32_t lane)
-{
-    if ((int32_t)ip < W.pos || (int32_t)(ip + k) > W.pos + (int32_t)D_WIN) dwin_fill(W, ip, lane);
-}
-__device__ __forceinline__ uint32_t dwin_byte(const DWin& W, uint32_t ip) { return W.w[(int32_t)ip - W.pos]; }
-
-__device__ __forceinline__ void warp_copy_lit(uint8_t* dst, const uint8_t* src, uint32_t n, uint32_t lane)
-{
-    if (n >= 64 && ((((uintptr_t)dst) ^ ((uintptr_t)src)) & 3) == 0) {
-        // same 4-byte phase: word copies in the middle
-        uint32_t head = (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3);
-        if (lane < head) dst[lane] = src[lane];
-        const uint32_t nw = (n - head) >> 2;
-        const uint32_t* s4 = reinterpret_cast<const uint32_t*>(src + head);
-        uint32_t* d4 = reinterpret_cast<uint32_t*>(dst + head);
-        for (uint32_t i = lane; i < nw; i += 32) d4[i] = s4[i];
-        for (uint32_t i = head + (nw << 2) + lane; i < n; i += 32) dst[i] = src[i];
-    } else {
-        for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
-    }
-}
-
-// returns decoded size or 0xFFFFFFFF on error.  `hist` = bytes of valid history before dst.
-__device__ uint32_t warp_decode_block(DWin& W, uint32_t srcSize, uint8_t* dst, uint32_t dstCap, uint64_t hist, uint32_t lane)
-{
-    uint32_t ip = 0, op = 0;
-    if (srcSize == 0) return 0xFFFFFFFFu;
-    for (;;) {
-        if (ip >= srcSize) return 0xFFFFFFFFu;
-        dwin_need(W, ip, 20, lane);                         // token + a few length bytes + short literals' head
-        const uint32_t token = dwin_byte(W, ip++);
-        uint32_t lit = token >> 4;
-        if (lit == 15) {
-            uint32_t b;
-            do { if (ip >= srcSize) return 0xFFFFFFFFu; dwin_need(W, ip, 1, lane); b = dwin_byte(W, ip++); lit += b; } while (b == 255);
-        }
-        if (lit > srcSize - ip || lit > dstCap - op) return 0xFFFFFFFFu;
-        if (lit) {
-            if (lit <= 256) {                               // short run: out of the window
-                dwin_need(W, ip, lit, lane);
-                const uint8_t* s = W.w + ((int32_t)ip - W.pos);
-                for (uint32_t i = lane; i < lit; i += 32) dst[op + i] = s[i];
-            } else warp_copy_lit(dst + op, W.gsrc + ip, lit, lane);
-        }
-        ip += lit; op += lit;
-        if (ip == srcSize) break;
-        if (srcSize - ip < 2) return 0xFFFFFFFFu;
-        dwin_need(W, ip, 3, lane);
-        const uint32_t off = dwin_byte(W, ip) | (dwin_byte(W, ip + 1) << 8);
-        ip += 2;
-        if (off == 0 || (uint64_t)off > (uint64_t)op + hist) return 0xFFFFFFFFu;
-        uint32_t ml = token & 15;
-        if (ml == 15) {
-            uint32_t b;
-            do { if (ip >= srcSize) return 0xFFFFFFFFu; dwin_need(W, ip, 1, lane); b = dwin_byte(W, ip++); ml += b; } while (b == 255);
-        }
-        ml += 4;
-        if (ml > dstCap - op) return 0xFFFFFFFFu;
-        __syncwarp();                                      // literals (and earlier matches) visible to all lanes
-        uint8_t* d = dst + op;
-        const uint8_t* m = d - off;
-        if (off >= ml) { for (uint32_t i = lane; i < ml; i += 32) d[i] = m[i]; }
-        else if (off >= 32) {                              // overlapping, period >= warp width: 32-byte waves
-            for (uint32_t i = 0; i < ml; i += 32) { if (i + lane < ml) d[i + lane] = m[i + lane]; __syncwarp(); }
-        } else {                                           // short period: replicate the pattern
-            for (uint32_t i = lane; i < ml; i += 32) d[i] = m[i % off];
-        }
-        op += ml;
-        __syncwarp();
-    }
-    return op;
-}
-
-__device__ __forceinline__ void d_fail(uint32_t* status, uint32_t f, uint32_t code, uint32_t lane)
-{
-    if (lane == 0) atomicCAS(&status[f], 0u, code);        // first error wins
-}
-
-// status[] and out_size[] must be zero on entry (the launcher clears them).
-__global__ void __launch_bounds__(32 * D_WARPS)
-lz4_decode_frames_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ in_end, const uint64_t* __restrict__ frame_off,
-                         const uint32_t* __restrict__ frame_csize, uint8_t* __restrict__ out, const uint64_t* __restrict__ out_off,
-                         unsigned long long* __restrict__ out_size, uint32_t* __restrict__ status, uint32_t* __restrict__ stored_chk,
-                         uint32_t nframes, uint32_t max_bpf)
-{
-    __shared__ __align__(16) uint8_t win[D_WARPS][D_WIN];
-    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint64_t gw = (uint64_t)blockIdx.x * D_WARPS + wid;
-    const uint32_t f = (uint32_t)(gw / max_bpf), slot = (uint32_t)(gw % max_bpf);
-    if (f >= nframes) return;
-    const uint8_t* p = in + frame_off[f] + 12;              // LZ4F frame (after the skippable header)
-    const uint32_t fs = frame_csize[f];
-    uint8_t* dst = out + out_off[f];
-    const uint64_t cap = out_off[f + 1] - out_off[f];
-    // ---- frame header (every warp of the frame re-reads it; only slot 0 reports header errors)
-    if (fs < 7 + 4) { if (slot == 0) d_fail(status, f, ZMT_ST_TRUNCATED, lane); return; }
-    if (ldg_le32(p) != 0x184D2204u) { if (slot == 0) d_fail(status, f, ZMT_ST_BAD_MAGIC, lane); return; }
-    const uint32_t flg = p[4], bd = p[5];
-    if ((flg >> 6) != 1 || (flg & 2) || (bd & 0x8F) || ((bd >> 4) & 7) < 4) { if (slot == 0) d_fail(status, f, ZMT_ST_BAD_HEADER, lane); return; }
-    const uint32_t indep = (flg >> 5) & 1, bchk = (flg >> 4) & 1, csz = (flg >> 3) & 1, cchk = (flg >> 2) & 1, did = flg & 1;
-    const uint32_t blkmax = 1u << (8 + 2 * ((bd >> 4) & 7));
-    const uint32_t hl = 2 + (csz ? 8 : 0) + (did ? 4 : 0);
-    if (fs < 4 + hl + 1 + 4) { if (slot == 0) d_fail(status, f, ZMT_ST_TRUNCATED, lane); return; }
-    if (slot == 0) {
-        uint8_t h[14];
-        for (uint32_t i = 0; i < hl; i++) h[i] = p[4 + i];
-        if (((xxh32_small(h, hl, 0) >> 8) & 0xFF) != p[4 + hl]) { d_fail(status, f, ZMT_ST_HDR_CHECKSUM, lane); return; }
-    }
-    if (!indep && slot != 0) return;                        // linked blocks: the frame's first warp does them all in order
-
-    DWin W; W.w = win[wid]; W.in_end = in_end;
-    uint32_t ip = 4 + hl + 1, b = 0;
-    uint64_t total = 0;                                     // output offset of the current block inside the frame
-    bool mine_done = false;
-    for (;;) {
-        if (fs - ip < 4) { d_fail(status, f, ZMT_ST_TRUNCATED, lane); return; }
-        const uint32_t bh = ldg_le32(p + ip);
-        if (bh == 0) {                                      // end mark
-            if (!indep || mine_done || b == 0) break;       // the warp that decoded the last block (or slot 0 of an empty frame) does the trailer
-            return;                                         // this slot is past the last block
-        }
-        if (indep && mine_done) {                           // another block follows mine: its own warp handles it ...
-            if (slot + 1 == max_bpf) d_fail(status, f, ZMT_ST_BLOCK, lane);   // ... unless there is none: more blocks than slots
-            return;
-        }
-        ip += 4;
-        const uint32_t bs = bh & 0x7FFFFFFFu;
-        if (bs > blkmax) { d_fail(status, f, ZMT_ST_BLOCK, lane); return; }
-        if (fs - ip < bs + (bchk ? 4 : 0)) { d_fail(status, f, ZMT_ST_TRUNCATED, lane); return; }
-        if (indep && b != slot) { ip += bs + (bchk ? 4 : 0); b++; total += blkmax; continue; }   // not my block: skip over it
-        if (total > cap) { d_fail(status, f, ZMT_ST_DST_SMALL, lane); return; }
-        uint32_t d;
-        if (bh & 0x80000000u) {
-            if (bs > cap - total) { d_fail(status, f, ZMT_ST_DST_SMALL, lane); return; }
-            warp_copy_lit(dst + total, p + ip, bs, lane);
-            d = bs;
-        } else {
-            const uint64_t room = cap - total;
-            const uint32_t dcap = room < blkmax ? (uint32_t)room : blkmax;
-            const uint64_t hist = indep ? 0 : (total < 65536 ? total : 65536);
-            W.gsrc = p + ip; W.pos = 0x40000000;            // empty window
-            d = warp_decode_block(W, bs, dst + total, dcap, hist, lane);
-            if (d == 0xFFFFFFFFu) { d_fail(status, f, ZMT_ST_BLOCK, lane); return; }
-        }
-        if (lane == 0) atomicAdd(&out_size[f], (unsigned long long)d);
-        ip += bs + (bchk ? 4 : 0);
-        if (indep) {
-            // one-warp-per-block addressing assumes every block but the last regenerates exactly blkmax bytes
-            // (true for liblz4 and for our encoder); anything else is reported, not guessed
-            mine_done = true;
-            if (d != blkmax) {
-                if (fs - ip < 4) { d_fail(status, f, ZMT_ST_TRUNCATED, lane); return; }
-                if (ldg_le32(p + ip) != 0) { d_fail(status, f, ZMT_ST_BLOCK, lane); return; }
-            }
-        }
-        total += d; b++;
-        __syncwarp();
-    }
-    // ---- trailer: end mark, optional content checksum, nothing after it
-    ip += 4;
-    uint32_t has_chk = 0, chkv = 0;
-    if (cchk) {
-        if (fs - ip < 4) { d_fail(status, f, ZMT_ST_TRUNCATED, lane); return; }
-        has_chk = 1; chkv = ldg_le32(p + ip); ip += 4;
-    }
-    if (ip != fs) { d_fail(status, f, ZMT_ST_TRAILING, lane); return; }
-    if (lane == 0) { stored_chk[f] = chkv; if (has_chk) atomicOr(&status[f], ZMT_ST_HAS_CHK); }
-}
-
-// content-size check + comparison of the recomputed XXH32 with the stored content checksum
-__global__ void lz4_verify_kernel(const uint8_t* __restrict__ in, const uint64_t* __restrict__ frame_off, const uint32_t* __restrict__ frame_csize,
-                                  uint32_t* __restrict__ status, const unsigned long long* __restrict__ out_size,
-                                  const uint32_t* __restrict__ stored_chk, const uint32_t* __restrict__ computed, uint32_t nframes)
-{
-    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= nframes) return;
-    uint32_t st = status[f];
-    if ((st & 0xFF) == ZMT_ST_OK) {
-        const uint8_t* p = in + frame_off[f] + 12;
-        if (frame_csize[f] >= 15 && (p[4] & 0x08) && ldg_le64(p + 6) != out_size[f]) st = ZMT_ST_CONTENT_SIZE;
-        else if ((st & ZMT_ST_HAS_CHK) && stored_chk[f] != computed[f]) st = ZMT_ST_CONTENT_CHECKSUM;
-    }
-    status[f] = st & 0xFF;
-}
+#include "lz4_decode.cuh"
 
 // ============================================================================ zstd frame pack
 // frame = 12 (skippable hdr) + magic 4 + FHD 1 + FCS (1 / 2 / 4) + the blocks of every 64 KiB window (+ an empty
@@ -988,9 +780,10 @@ static void zstd_build_ctable(ZFseCTable& T, const int16_t* norm, int nsym, int 
 
 static int zstd_tables_init()
 {
-    static std::vector<int> done;                 // devices whose __constant__ copies are loaded
-    int dev = 0; if (cudaGetDevice(&dev) != cudaSuccess) return ZMT_ST_CUDA;
-    for (int d : done) if (d == dev) return ZMT_ST_OK;
+    static std::mutex mu; static bool done[64];   // devices whose __constant__ copies are loaded (contexts may run on several host threads)
+    int dev = 0; if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return ZMT_ST_CUDA;
+    std::lock_guard<std::mutex> guard(mu);
+    if (done[dev]) return ZMT_ST_OK;
     static const int16_t LLn[36] = { 4,3,2,2,2,2,2,2,2,2,2,2,2,1,1,1,2,2,2,2,2,2,2,2,2,3,2,1,1,1,1,1,-1,-1,-1,-1 };
     static const int16_t MLn[53] = { 1,4,3,2,2,2,2,2,2,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,-1,-1,-1,-1,-1,-1,-1 };
     static const int16_t OFn[29] = { 1,1,1,1,1,1,2,2,2,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,-1,-1,-1,-1,-1 };
@@ -1009,7 +802,8 @@ static int zstd_tables_init()
     cudaMemcpyToSymbol(c_ll_base, LLb, sizeof(LLb)); cudaMemcpyToSymbol(c_ml_base, MLb, sizeof(MLb));
     cudaMemcpyToSymbol(c_ll_bits, LLx, sizeof(LLx)); cudaMemcpyToSymbol(c_ml_bits, MLx, sizeof(MLx));
     if (cudaGetLastError() != cudaSuccess) return ZMT_ST_CUDA;
-    done.push_back(dev);
+    if (cudaDeviceSynchronize() != cudaSuccess) return ZMT_ST_CUDA;    // the kernels run on non-blocking streams: nothing else orders the table copies before them
+    done[dev] = true;
     return ZMT_ST_OK;
 }
 
@@ -1061,11 +855,15 @@ static bool zmt_dbg_check(cudaStream_t st, const char* what)
     return true;
 }
 
+static std::mutex g_dev_mu;                     // guards the per-device lazy state below (contexts may run on several host threads)
 static inline int zmt_sm_count()
 {
-    static int n = 0;
-    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
-    return n;
+    static int n[64];
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 148;
+    std::lock_guard<std::mutex> g(g_dev_mu);
+    if (!n[dev]) { cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev); if (n[dev] <= 0) n[dev] = 148; }
+    return n[dev];
 }
 
 extern "C" uint32_t zmt_chunk_count(uint64_t in_bytes, uint32_t chunk_size)
@@ -1205,33 +1003,60 @@ extern "C" int zmt_zstd_compress_device(const void* d_in, uint64_t in_bytes, uin
     return cudaGetLastError() == cudaSuccess ? ZMT_ST_OK : ZMT_ST_CUDA;
 }
 
-extern "C" size_t zmt_lz4d_workspace_bytes(uint32_t nframes)
+static inline uint64_t a256(uint64_t x) { return (x + 255) & ~255ull; }
+
+// workspace: stored[] | computed[] | needs_seq[] | ticket | slot counts | first_slot | block table | progress | match records
+extern "C" size_t zmt_lz4d_workspace_bytes(uint32_t nframes, uint32_t nslots, uint64_t in_bytes)
 {
-    return (size_t)((((uint64_t)nframes * 4 + 255) & ~255ull) * 2 + 1024);
+    uint64_t sz = 3 * a256((uint64_t)nframes * 4) + 256 + 2 * a256(((uint64_t)nframes + 1) * 8);
+    sz += a256((uint64_t)nslots * sizeof(LzBlk)) + a256((uint64_t)nslots * 4);
+    sz += a256((in_bytes / 3 + 8) * 8);
+    return (size_t)sz + 1024;
 }
 
 extern "C" int zmt_lz4_decompress_device(const void* d_in, uint64_t in_bytes, const uint64_t* d_frame_off, const uint32_t* d_frame_csize, uint32_t nframes,
-                                         uint32_t max_blocks_per_frame, void* d_out, const uint64_t* d_out_off, uint64_t* d_out_size,
+                                         uint32_t nslots, void* d_out, const uint64_t* d_out_off, uint64_t* d_out_size,
                                          uint32_t* d_status, void* d_work, void* stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (nframes == 0) return ZMT_ST_OK;
-    if (max_blocks_per_frame == 0) max_blocks_per_frame = 1;
+    if (nslots < nframes) return ZMT_ST_BAD_ARG;
     uint8_t* w = (uint8_t*)d_work;
-    uint32_t* stored = (uint32_t*)w; w += (((uint64_t)nframes * 4 + 255) & ~255ull);
-    uint32_t* computed = (uint32_t*)w;
+    uint32_t* stored = (uint32_t*)w; w += a256((uint64_t)nframes * 4);
+    uint32_t* computed = (uint32_t*)w; w += a256((uint64_t)nframes * 4);
+    uint32_t* needs_seq = (uint32_t*)w; w += a256((uint64_t)nframes * 4);
+    unsigned int* ticket = (unsigned int*)w; w += 256;
+    uint64_t* slot_cnt = (uint64_t*)w; w += a256(((uint64_t)nframes + 1) * 8);
+    uint64_t* first_slot = (uint64_t*)w; w += a256(((uint64_t)nframes + 1) * 8);
+    LzBlk* tab = (LzBlk*)w; w += a256((uint64_t)nslots * sizeof(LzBlk));
+    uint32_t* prog = (uint32_t*)w; w += a256((uint64_t)nslots * 4);
+    unsigned long long* rec = (unsigned long long*)w;
     cudaMemsetAsync(d_status, 0, (size_t)nframes * 4, stream);
     cudaMemsetAsync(d_out_size, 0, (size_t)nframes * 8, stream);
-    cudaMemsetAsync(stored, 0, (size_t)nframes * 4, stream);
-    const uint64_t nwarps = (uint64_t)nframes * max_blocks_per_frame;
-    if ((nwarps + D_WARPS - 1) / D_WARPS > 0x7FFFFFFFull) return ZMT_ST_BAD_ARG;
+    cudaMemsetAsync(stored, 0, 3 * a256((uint64_t)nframes * 4) + 256, stream);      // stored, computed, needs_seq, ticket
+    const uint8_t* in = (const uint8_t*)d_in;
+    lz4_slot_counts_kernel<<<(nframes + 255) / 256, 256, 0, stream>>>(d_out_off, nframes, slot_cnt);
+    scan_u64_kernel<<<1, 1024, 0, stream>>>(slot_cnt, first_slot, nframes);
+    lz4_scan_frames_kernel<<<(nframes + 127) / 128, 128, 0, stream>>>(in, d_frame_off, d_frame_csize, d_out_off, first_slot, nslots, tab, prog, d_status, stored, needs_seq, nframes);
+    zmt_dbg_check(stream, "lz4_scan_frames_kernel");
     { ZmtProfScope ps(ZMT_K_LZ4_DECODE, stream);
-    lz4_decode_frames_kernel<<<(uint32_t)((nwarps + D_WARPS - 1) / D_WARPS), 32 * D_WARPS, 0, stream>>>(
-        (const uint8_t*)d_in, (const uint8_t*)d_in + in_bytes, d_frame_off, d_frame_csize, (uint8_t*)d_out, d_out_off,
-        (unsigned long long*)d_out_size, d_status, stored, nframes, max_blocks_per_frame); }
+    lz4_parse_blocks_kernel<<<(nslots + LZD_WARPS - 1) / LZD_WARPS, 32 * LZD_WARPS, 0, stream>>>(
+        in, in + in_bytes, d_frame_off, (uint8_t*)d_out, d_out_off, first_slot, tab, rec, (unsigned long long*)d_out_size, d_status, needs_seq, nframes, nslots); }
+    zmt_dbg_check(stream, "lz4_parse_blocks_kernel");
+    {
+        const uint32_t maxg = (uint32_t)(zmt_sm_count() * 8);
+        const uint32_t need = (nslots + LZD_WARPS - 1) / LZD_WARPS;
+        ZmtProfScope ps(ZMT_K_LZ4_DEXEC, stream);
+        lz4_exec_blocks_kernel<<<need < maxg ? need : maxg, 32 * LZD_WARPS, 0, stream>>>(
+            (uint8_t*)d_out, d_out_off, d_frame_off, first_slot, tab, rec, prog, d_status, needs_seq, ticket, nframes, nslots);
+    }
+    zmt_dbg_check(stream, "lz4_exec_blocks_kernel");
+    lz4_decode_frames_seq_kernel<<<(nframes + LZD_WARPS - 1) / LZD_WARPS, 32 * LZD_WARPS, 0, stream>>>(
+        in, in + in_bytes, d_frame_off, d_frame_csize, (uint8_t*)d_out, d_out_off, (unsigned long long*)d_out_size, d_status, needs_seq, nframes);
+    zmt_dbg_check(stream, "lz4_decode_frames_seq_kernel");
     { ZmtProfScope ps(ZMT_K_XXH32_DEC, stream);
     xxh32_kernel<<<(nframes + X_WARPS - 1) / X_WARPS, 32 * X_WARPS, 0, stream>>>((const uint8_t*)d_out, d_out_off, d_out_size, nullptr, 0, 0, computed, nframes); }
-    lz4_verify_kernel<<<(nframes + 255) / 256, 256, 0, stream>>>((const uint8_t*)d_in, d_frame_off, d_frame_csize, d_status,
+    lz4_verify_kernel<<<(nframes + 255) / 256, 256, 0, stream>>>(in, d_frame_off, d_frame_csize, d_status,
                                                                 (const unsigned long long*)d_out_size, stored, computed, nframes);
     return cudaGetLastError() == cudaSuccess ? ZMT_ST_OK : ZMT_ST_CUDA;
 }

@@ -21,6 +21,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <mutex>
 #include <vector>
 #include "common.cuh"
 #include "zmt_dev.h"
@@ -571,9 +572,10 @@ static void zd_build_dtable(ZFseDTable& T, const int16_t* norm, int nsym, int lo
 
 static int zd_tables_init()
 {
-    static std::vector<int> done;
-    int dev = 0; if (cudaGetDevice(&dev) != cudaSuccess) return ZMT_ST_CUDA;
-    for (int d : done) if (d == dev) return ZMT_ST_OK;
+    static std::mutex mu; static bool done[64];   // devices whose __constant__ copies are loaded (contexts may run on several host threads)
+    int dev = 0; if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return ZMT_ST_CUDA;
+    std::lock_guard<std::mutex> guard(mu);
+    if (done[dev]) return ZMT_ST_OK;
     static const int16_t LLn[36] = { 4,3,2,2,2,2,2,2,2,2,2,2,2,1,1,1,2,2,2,2,2,2,2,2,2,3,2,1,1,1,1,1,-1,-1,-1,-1 };
     static const int16_t MLn[53] = { 1,4,3,2,2,2,2,2,2,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,-1,-1,-1,-1,-1,-1,-1 };
     static const int16_t OFn[29] = { 1,1,1,1,1,1,2,2,2,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,-1,-1,-1,-1,-1 };
@@ -588,7 +590,8 @@ static int zd_tables_init()
     cudaMemcpyToSymbol(d_ll_base, LLb, sizeof(LLb)); cudaMemcpyToSymbol(d_ml_base, MLb, sizeof(MLb));
     cudaMemcpyToSymbol(d_ll_bits, LLx, sizeof(LLx)); cudaMemcpyToSymbol(d_ml_bits, MLx, sizeof(MLx));
     if (cudaGetLastError() != cudaSuccess) return ZMT_ST_CUDA;
-    done.push_back(dev);
+    if (cudaDeviceSynchronize() != cudaSuccess) return ZMT_ST_CUDA;    // the kernels run on non-blocking streams: nothing else orders the table copies before them
+    done[dev] = true;
     return ZMT_ST_OK;
 }
 
