@@ -17,6 +17,9 @@ extern "C" {
 /* ---- synthetic inputs (harness/datagen.c) ---- */
 void zmt_gen_chunk(int kind, uint64_t chunk_index, uint8_t* buf, size_t n);
 void zmt_gen_stream(int kind, uint64_t first, uint64_t stride, size_t chunk, uint8_t* buf, size_t total, int nthreads);
+/* share of consumer `rank` of `world` when the global stream is dealt round-robin in batches of `batch` chunks:
+ * local chunk c = global chunk (c / batch) * batch * world + rank * batch + c % batch */
+void zmt_gen_stream_dealt(int kind, uint64_t rank, uint64_t world, uint64_t batch, size_t chunk, uint8_t* buf, size_t total, int nthreads);
 
 /* ---- memory-to-memory drivers of the callback API (harness/memio_glue.c) ----
  * stats[0..4] = bytes written, frames, Insize counter, Outsize counter, (reads<<32 | writes) */

@@ -39,6 +39,17 @@ def test_library_exports_every_declared_symbol():
     assert " B zstdmt_errcode" in out or " D zstdmt_errcode" in out
 
 
+def test_harness_libraries_export_their_header_and_product_does_not():
+    """include/zstdmt_b200_harness.h: generator and in-memory callback drivers live outside the product library."""
+    txt = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "zstdmt_b200_harness.h")).read(), flags=re.S)
+    names = sorted(set(m.group(1) for m in re.finditer(r"\b(zmt_\w+)\s*\(", txt)))
+    assert len(names) >= 7
+    G, M, L = z.gen_lib(), z.memio_lib(), z.lib()
+    for s in names:
+        assert hasattr(G, s) or hasattr(M, s), "missing harness export: " + s
+        assert not hasattr(L, s), "harness symbol leaked into the product library: " + s
+
+
 def test_create_validates_like_reference():
     L = z.lib()
     # lz4-mt_compress.c:103-108 / lz4-mt_decompress.c:101-102
@@ -129,3 +140,23 @@ def test_zstd_host_block_scan_on_reference_frames(level, kind):
         rc = L.zmt_zstd_scan_frame_host(fr2.ctypes.data, fr2.size, 0, i, blocks.ctypes.data, ctypes.byref(nb2), cap, ctypes.byref(s2), ctypes.byref(cs), ctypes.byref(nsq))
         assert rc != 0
     assert total == n
+
+
+def test_zstd_host_scan_flags_checksum_and_missing_content_size():
+    """Frames as the stock zstd CLI / a streaming producer writes them: the host scan accounts for the 4 checksum bytes,
+    reports flag 2 (checksum) / 4 (no content size) and, without a content size, an upper bound of the output."""
+    import ctypes
+    import test_gpu_plain_streams as t
+    L = z.lib()
+    src = z.gen_stream(z.GEN_MIX, 700000, 1 << 20)
+    dsz = L.zmt_zstd_blk_desc_bytes()
+    for fr, want_flags, exact in ((t.zstd_adv(src, 3, checksum=1), 2, True), (t.zstd_adv(src, 3, checksum=0, pieces=[300000, 400000]), 4, False),
+                                  (t.zstd_adv(src, 3, checksum=1, pieces=[1, 699999]), 6, False)):
+        cap = fr.size // 3 + 16
+        blocks = np.zeros(cap * dsz, np.uint8)
+        nblk = ctypes.c_uint32(0); scr = ctypes.c_uint64(0); cs = ctypes.c_uint64(0); fl = ctypes.c_uint32(0)
+        rc = L.zmt_zstd_scan_frame_host(fr.ctypes.data, fr.size, 0, 0, blocks.ctypes.data, ctypes.byref(nblk), cap, ctypes.byref(scr), ctypes.byref(cs), ctypes.byref(fl))
+        assert rc == 0 and (fl.value & 6) == want_flags
+        assert cs.value == src.size if exact else cs.value >= src.size
+        nb2 = ctypes.c_uint32(0); s2 = ctypes.c_uint64(0)
+        assert L.zmt_zstd_scan_frame_host(fr.ctypes.data, fr.size - 1, 0, 0, blocks.ctypes.data, ctypes.byref(nb2), cap, ctypes.byref(s2), ctypes.byref(cs), ctypes.byref(fl)) != 0

@@ -97,6 +97,8 @@ def gen_lib():
         G = ctypes.CDLL(GEN_LIB_PATH)
         G.zmt_gen_stream.restype = None
         G.zmt_gen_stream.argtypes = [ctypes.c_int, c_u64, c_u64, c_sz, c_vp, c_sz, ctypes.c_int]
+        G.zmt_gen_stream_dealt.restype = None
+        G.zmt_gen_stream_dealt.argtypes = [ctypes.c_int, c_u64, c_u64, c_u64, c_sz, c_vp, c_sz, ctypes.c_int]
         _gen = G
     return _gen
 
@@ -121,13 +123,16 @@ def memio_lib():
 
 
 # ------------------------------------------------------------------ synthetic inputs
-def gen_stream(kind, nbytes, chunk, first=0, stride=1, threads=None, out=None):
-    """Deterministic synthetic stream (harness/datagen.c).  Returns a numpy uint8 array."""
+def gen_stream(kind, nbytes, chunk, first=0, stride=1, threads=None, out=None, deal=None):
+    """Deterministic synthetic stream (harness/datagen.c).  Returns a numpy uint8 array.
+    deal=(rank, world, batch): the share of consumer `rank` when the global stream is dealt in batches of chunks."""
     if out is None:
         out = np.empty(nbytes, dtype=np.uint8)
     if threads is None:
         threads = min(32, os.cpu_count() or 1)
-    if nbytes:
+    if nbytes and deal is not None:
+        gen_lib().zmt_gen_stream_dealt(kind, deal[0], deal[1], deal[2], chunk, out.ctypes.data, nbytes, threads)
+    elif nbytes:
         gen_lib().zmt_gen_stream(kind, first, stride, chunk, out.ctypes.data, nbytes, threads)
     return out
 

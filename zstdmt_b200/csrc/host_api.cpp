@@ -518,17 +518,6 @@ bool lz4f_out_size(const uint8_t* p, size_t n, uint64_t* out)
     *out = total; return true;
 }
 
-bool zstd_out_size(const uint8_t* p, size_t n, uint64_t* out)
-{
-    if (n < 6 || rd32(p) != ZSTD_MAGIC) return false;
-    const uint32_t fhd = p[4], fcs = fhd >> 6, single = (fhd >> 5) & 1, did = fhd & 3;
-    size_t pos = 5 + (single ? 0 : 1) + (did == 0 ? 0 : did == 1 ? 1 : did == 2 ? 2 : 4);
-    const size_t fl = fcs == 0 ? (single ? 1 : 0) : fcs == 1 ? 2 : fcs == 2 ? 4 : 8;
-    if (fl == 0 || n < pos + fl) return false;
-    if (fl == 1) *out = p[pos]; else if (fl == 2) *out = (uint64_t)(p[pos] | (p[pos + 1] << 8)) + 256; else if (fl == 4) *out = rd32(p + pos); else *out = rd64(p + pos);
-    return true;
-}
-
 // reads exactly `want` bytes unless EOF; returns 0 ok / error; *got = delivered
 size_t read_some(const ErrCodes& E, GenRdWr* rw, void* dst, size_t want, size_t* got)
 {
@@ -542,115 +531,164 @@ size_t read_some(const ErrCodes& E, GenRdWr* rw, void* dst, size_t want, size_t*
 // ------------------------------------------------------------------ plain (unframed) single streams
 // What the reference routes to st_decompress (lz4-mt_decompress.c:391-483, zstd-mt_decompress.c:552-687): an ordinary
 // .lz4 / .zst file, i.e. codec frames back to back without the 12-byte size headers.  Frame lengths are only known after
-// walking the block headers, so this path is one-shot: read to EOF, scan on the host, decode everything on the GPU with
-// the same kernels, write.  `first`/`have` = the bytes already consumed by the stream-type sniffing.
-struct DevBuf { void* p = nullptr; ~DevBuf() { if (p) cudaFree(p); } bool alloc(size_t n) { return cudaMalloc(&p, n ? n : 1) == cudaSuccess; } };
+// walking the block headers, so the host reads ahead, cuts the bytes it holds into complete frames, and decodes them in
+// batches of at most ~kPlainBatch input bytes with the same GPU kernels; the consumed bytes are dropped before the next
+// read, so memory is bounded by the batch size or by the largest single frame, whichever is larger (the reference streams
+// through two fixed buffers; a frame here must fit in host and device memory as a whole).  `first`/`have` = the bytes
+// already consumed by the stream-type sniffing.
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    bool need(size_t n) {                                   // grow-only
+        if (n <= cap && p) return true;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        const size_t want = n + n / 4 + 4096;
+        if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); if (cudaMalloc(&p, n ? n : 1) != cudaSuccess) { cudaGetLastError(); p = nullptr; return false; } cap = n; return true; }
+        cap = want; return true;
+    }
+};
 
 size_t decompress_single_stream(Ctx* c, GenRdWr* rw, const uint8_t* first, size_t have)
 {
     const ErrCodes& E = *c->E;
     const bool is_zstd = c->codec == CODEC_ZSTD;
+    const size_t kPlainBatch = env_size("ZSTDMT_B200_PLAIN_MB", 64) << 20;
+    const size_t piece = c->inputsize < (64u << 10) ? (size_t)1 << 20 : c->inputsize;
+    const size_t dsz = zmt_zstd_blk_desc_bytes();
     std::vector<uint8_t> in(12, 0);                         // 12 pad bytes: the LZ4 kernel addresses a frame as base + off + 12
     in.insert(in.end(), first, first + have);
-    size_t piece = c->inputsize < (64u << 10) ? (size_t)1 << 20 : c->inputsize;
-    for (;;) {
-        const size_t old = in.size();
-        in.resize(old + piece);
-        size_t got = 0;
-        size_t e = read_some(E, rw, in.data() + old, piece, &got);
-        in.resize(old + got);
-        if (e) return e;
-        if (got == 0) break;
-    }
-    const uint8_t* s = in.data() + 12; const size_t n = in.size() - 12;
-    c->insize = n;                                          // every byte of the stream, sniffed bytes included
-    // ---- host scan: frame table (+ zstd block table)
-    std::vector<uint64_t> foff, ooff(1, 0), expect; std::vector<uint32_t> fcs, first_blk(1, 0), fseq;
-    std::vector<uint8_t> blocks; uint32_t nblk = 0; uint64_t scratch = 0; uint64_t nslots = 0;
-    const size_t dsz = zmt_zstd_blk_desc_bytes();
-    if (is_zstd) blocks.resize((n / 3 + 16) * dsz);
-    size_t pos = 0;
-    while (pos < n) {
-        if (n - pos < 4) return E.data_error;
-        const uint32_t magic = rd32(s + pos);
-        if ((magic & 0xFFFFFFF0u) == 0x184D2A50u) {          // skippable frame: magic, LE32 size, payload
-            if (n - pos < 8 || n - pos - 8 < rd32(s + pos + 4)) return E.data_error;
-            pos += 8 + (size_t)rd32(s + pos + 4); continue;
-        }
-        if (!is_zstd) {
-            if (magic != LZ4F_MAGIC || n - pos < 7) return E.data_error;
-            const uint32_t flg = s[pos + 4], bd = s[pos + 5], id = (bd >> 4) & 7;
-            if ((flg >> 6) != 1 || id < 4) { c->lib_errcode = ZMT_ST_BAD_HEADER; return E.library; }
-            const uint64_t blkmax = 1ull << (8 + 2 * id);
-            size_t q = pos + 4 + 2 + ((flg & 8) ? 8 : 0) + ((flg & 1) ? 4 : 0) + 1;
-            uint64_t bound = 0;
-            for (;;) {
-                if (q + 4 > n) { c->lib_errcode = ZMT_ST_TRUNCATED; return E.frame_decompress; }
-                const uint32_t bh = rd32(s + q); q += 4;
-                if (bh == 0) break;
-                const uint32_t bs = bh & 0x7FFFFFFFu;
-                bound += (bh & 0x80000000u) ? bs : blkmax;
-                q += (size_t)bs + ((flg & 0x10) ? 4 : 0);
-            }
-            if (flg & 4) q += 4;
-            if (q > n) { c->lib_errcode = ZMT_ST_TRUNCATED; return E.frame_decompress; }
-            const uint64_t osz = (flg & 8) ? rd64(s + pos + 6) : bound;
-            foff.push_back(pos); fcs.push_back((uint32_t)(q - pos)); ooff.push_back(ooff.back() + osz);
-            { const uint64_t nb = (osz + 65535) / 65536; nslots += nb ? nb : 1; }
-            pos = q;
-        } else {
-            if (magic < 0xFD2FB522u || magic > 0xFD2FB528u) return E.data_error;
-            uint64_t cs = 0; uint32_t nsq = 0; size_t used = 0;
-            const int zr = zmt_zstd_scan_frame_host2(s + pos, n - pos, 12 + pos, (uint32_t)foff.size(), blocks.data(), &nblk, (uint32_t)(blocks.size() / dsz), &scratch, &cs, &nsq, &used);
-            if (zr != ZMT_ST_OK) { c->lib_errcode = (size_t)zr; return zr == ZMT_ST_TRUNCATED ? E.frame_decompress : E.library; }
-            foff.push_back(pos); expect.push_back(cs); fseq.push_back(nsq); first_blk.push_back(nblk); ooff.push_back(ooff.back() + cs);
-            pos += used;
-        }
-    }
-    const uint32_t nf = (uint32_t)foff.size();
-    if (nf == 0) return 0;
-    // ---- one-shot device decode
+    bool eof = false;
+    size_t pos = 0;                                         // parse position inside in[12..]
     const std::vector<int> devs = env_devices();
     if (devs.empty() || cudaSetDevice(devs[0]) != cudaSuccess) { c->lib_errcode = ZMT_ST_CUDA; return E.library; }
-    const uint64_t total = ooff.back();
     DevBuf d_in, d_out, d_tab, d_blk, d_work;
-    const size_t tab_bytes = tables_bytes(nf);
-    std::vector<uint8_t> h_tab(tab_bytes);
-    Tables T = tables_at(h_tab.data(), nf);
-    for (uint32_t i = 0; i < nf; i++) { T.a[i] = foff[i]; T.b[i] = ooff[i]; if (is_zstd) { T.f[i] = expect[i]; T.d[i] = fseq[i]; T.g[i] = first_blk[i]; } else T.d[i] = fcs[i]; }
-    T.b[nf] = total; if (is_zstd) T.g[nf] = nblk;
-    const size_t wk = is_zstd ? zmt_zstdd_workspace_bytes(nf, nblk, scratch) : zmt_lz4d_workspace_bytes(nf, (uint32_t)nslots, in.size());
-    if (!d_in.alloc(in.size() + 256) || !d_out.alloc(total + 256) || !d_tab.alloc(tab_bytes) || !d_work.alloc(wk) || (is_zstd && !d_blk.alloc((size_t)nblk * dsz))) { cudaGetLastError(); return E.mem; }
     cudaStream_t st = nullptr;
     if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { c->lib_errcode = ZMT_ST_CUDA; return E.library; }
-    Tables Td = tables_at((uint8_t*)d_tab.p, nf);
-    cudaMemcpyAsync(d_in.p, in.data(), in.size(), cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(d_tab.p, h_tab.data(), tab_bytes, cudaMemcpyHostToDevice, st);
-    if (is_zstd && nblk) cudaMemcpyAsync(d_blk.p, blocks.data(), (size_t)nblk * dsz, cudaMemcpyHostToDevice, st);
-    const int rc = is_zstd ? zmt_zstd_decompress_device(d_in.p, d_blk.p, nblk, Td.g, Td.f, Td.d, nf, d_out.p, Td.b, Td.c, Td.e, d_work.p, st)
-                           : zmt_lz4_decompress_device(d_in.p, in.size(), Td.a, Td.d, nf, (uint32_t)nslots, d_out.p, Td.b, Td.c, Td.e, d_work.p, st);
-    std::vector<uint8_t> out(total ? total : 1);
-    std::vector<uint32_t> status(nf); std::vector<uint64_t> osz(nf);
-    cudaError_t ce = cudaSuccess;
-    if (rc == ZMT_ST_OK) {
-        if (total) ce = cudaMemcpyAsync(out.data(), d_out.p, total, cudaMemcpyDeviceToHost, st);
-        if (ce == cudaSuccess) ce = cudaMemcpyAsync(status.data(), Td.e, (size_t)nf * 4, cudaMemcpyDeviceToHost, st);
-        if (ce == cudaSuccess) ce = cudaMemcpyAsync(osz.data(), Td.c, (size_t)nf * 8, cudaMemcpyDeviceToHost, st);
-        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
-    }
-    cudaStreamDestroy(st);
-    if (rc != ZMT_ST_OK || ce != cudaSuccess) { c->lib_errcode = ZMT_ST_CUDA; return E.library; }
-    for (uint32_t i = 0; i < nf; i++) {
-        if (status[i] != ZMT_ST_OK) { c->lib_errcode = status[i]; return (status[i] == ZMT_ST_TRUNCATED || status[i] == ZMT_ST_TRAILING) ? E.frame_decompress : E.library; }
-        // frame by frame, in pieces of at most `piece` bytes (st_decompress writes as it goes)
-        uint64_t o = 0;
-        while (o < osz[i]) {
-            GenBuffer b; b.buf = out.data() + ooff[i] + o; b.size = (size_t)((osz[i] - o) < piece ? (osz[i] - o) : piece); b.allocated = b.size;
-            const size_t want = b.size;
-            const int rv = rw->fn_write(rw->arg_write, &b);
-            if (rv != 0) return mt_error(E, rv);
-            c->outsize += b.size; o += want;
+    struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } guard{st};
+    std::vector<uint8_t> out, blocks, h_tab;
+    std::vector<uint64_t> foff, ooff, expect; std::vector<uint32_t> fcs, first_blk, fflags;
+    c->insize = have;
+
+    for (;;) {
+        // ---- cut complete frames out of what we hold, up to one batch
+        foff.clear(); ooff.assign(1, 0); expect.clear(); fcs.clear(); first_blk.assign(1, 0); fflags.clear();
+        uint32_t nblk = 0; uint64_t scratch = 0, nslots = 0;
+        const size_t batch_start = pos;
+        bool need_more = false;
+        while (!need_more) {
+            const uint8_t* s = in.data() + 12; const size_t n = in.size() - 12;
+            if (pos >= n) { need_more = !eof; break; }
+            if (!foff.empty() && pos - batch_start >= kPlainBatch) break;
+            if (n - pos < 4) { if (eof) return E.data_error; need_more = true; break; }
+            const uint32_t magic = rd32(s + pos);
+            if ((magic & 0xFFFFFFF0u) == 0x184D2A50u) {          // skippable frame: magic, LE32 size, payload
+                if (n - pos < 8 || n - pos - 8 < rd32(s + pos + 4)) { if (eof) return E.data_error; need_more = true; break; }
+                pos += 8 + (size_t)rd32(s + pos + 4); continue;
+            }
+            if (!is_zstd) {
+                if (magic != LZ4F_MAGIC) return E.data_error;
+                if (n - pos < 7) { if (eof) return E.data_error; need_more = true; break; }
+                const uint32_t flg = s[pos + 4], bd = s[pos + 5], id = (bd >> 4) & 7;
+                if ((flg >> 6) != 1 || id < 4) { c->lib_errcode = ZMT_ST_BAD_HEADER; return E.library; }
+                const uint64_t blkmax = 1ull << (8 + 2 * id);
+                size_t q = pos + 4 + 2 + ((flg & 8) ? 8 : 0) + ((flg & 1) ? 4 : 0) + 1;
+                uint64_t bound = 0; bool cut = false;
+                for (;;) {
+                    if (q + 4 > n) { cut = true; break; }
+                    const uint32_t bh = rd32(s + q); q += 4;
+                    if (bh == 0) break;
+                    const uint32_t bs = bh & 0x7FFFFFFFu;
+                    bound += (bh & 0x80000000u) ? bs : blkmax;
+                    q += (size_t)bs + ((flg & 0x10) ? 4 : 0);
+                }
+                if (!cut && (flg & 4)) q += 4;
+                if (cut || q > n) { if (eof) { c->lib_errcode = ZMT_ST_TRUNCATED; return E.frame_decompress; } need_more = true; break; }
+                uint64_t osz = bound;
+                if (flg & 8) { osz = rd64(s + pos + 6); if (osz > bound) { c->lib_errcode = ZMT_ST_CONTENT_SIZE; return E.library; } }    // untrusted field, bounded by the block walk
+                foff.push_back(pos); fcs.push_back((uint32_t)(q - pos)); ooff.push_back(ooff.back() + osz);
+                { const uint64_t nb = (osz + 65535) / 65536; nslots += nb ? nb : 1; }
+                pos = q;
+            } else {
+                if (magic < 0xFD2FB522u || magic > 0xFD2FB528u) return E.data_error;
+                uint64_t cs = 0; uint32_t fl = 0; size_t used = 0;
+                const uint32_t nblk0 = nblk; const uint64_t scr0 = scratch;
+                int zr;
+                for (;;) {
+                    nblk = nblk0; scratch = scr0;
+                    zr = zmt_zstd_scan_frame_host2(s + pos, n - pos, 12 + pos, (uint32_t)foff.size(), blocks.data(), &nblk, (uint32_t)(blocks.size() / dsz), &scratch, &cs, &fl, &used);
+                    if (zr != ZMT_ST_DST_SMALL) break;
+                    blocks.resize(blocks.size() * 2 + 4096 * dsz);            // block table full: grow and rescan this frame
+                }
+                if (zr == ZMT_ST_TRUNCATED && !eof) { nblk = nblk0; scratch = scr0; need_more = true; break; }
+                if (zr != ZMT_ST_OK) { c->lib_errcode = (size_t)zr; return zr == ZMT_ST_TRUNCATED ? E.frame_decompress : E.library; }
+                foff.push_back(pos); expect.push_back((fl & 4u) ? ~0ull : cs); fflags.push_back(fl); first_blk.push_back(nblk); ooff.push_back(ooff.back() + cs);
+                pos += used;
+            }
         }
+        const uint32_t nf = (uint32_t)foff.size();
+        if (nf == 0) {
+            if (!need_more) break;                                            // EOF, everything consumed
+        } else {
+            // ---- decode this batch
+            const uint64_t total = ooff.back();
+            const size_t in_bytes = pos + 12;                                   // frames address the buffer from its 12-byte pad
+            const size_t tab_bytes = tables_bytes(nf);
+            h_tab.resize(tab_bytes);
+            Tables T = tables_at(h_tab.data(), nf);
+            for (uint32_t i = 0; i < nf; i++) { T.a[i] = foff[i]; T.b[i] = ooff[i]; if (is_zstd) { T.f[i] = expect[i]; T.d[i] = fflags[i]; T.g[i] = first_blk[i]; } else T.d[i] = fcs[i]; }
+            T.b[nf] = total; if (is_zstd) T.g[nf] = nblk;
+            const size_t wk = is_zstd ? zmt_zstdd_workspace_bytes(nf, nblk, scratch) : zmt_lz4d_workspace_bytes(nf, (uint32_t)nslots, in_bytes);
+            if (!d_in.need(in_bytes + 256) || !d_out.need(total + 256) || !d_tab.need(tab_bytes) || !d_work.need(wk) || (is_zstd && !d_blk.need((size_t)nblk * dsz + 16))) return E.mem;
+            Tables Td = tables_at((uint8_t*)d_tab.p, nf);
+            // only the bytes of this batch travel (the device addresses them at their buffer offsets)
+            const size_t lo = 12 + batch_start, hi = in_bytes;
+            cudaMemcpyAsync((uint8_t*)d_in.p + lo, in.data() + lo, hi - lo, cudaMemcpyHostToDevice, st);
+            cudaMemcpyAsync(d_tab.p, h_tab.data(), tab_bytes, cudaMemcpyHostToDevice, st);
+            if (is_zstd && nblk) cudaMemcpyAsync(d_blk.p, blocks.data(), (size_t)nblk * dsz, cudaMemcpyHostToDevice, st);
+            const int rc = is_zstd ? zmt_zstd_decompress_device(d_in.p, d_blk.p, nblk, Td.g, Td.f, Td.d, nf, d_out.p, Td.b, Td.c, Td.e, d_work.p, st)
+                                   : zmt_lz4_decompress_device(d_in.p, in_bytes, Td.a, Td.d, nf, (uint32_t)nslots, d_out.p, Td.b, Td.c, Td.e, d_work.p, st);
+            out.resize(total ? total : 1);
+            std::vector<uint32_t> status(nf); std::vector<uint64_t> osz(nf);
+            cudaError_t ce = cudaSuccess;
+            if (rc == ZMT_ST_OK) {
+                if (total) ce = cudaMemcpyAsync(out.data(), d_out.p, total, cudaMemcpyDeviceToHost, st);
+                if (ce == cudaSuccess) ce = cudaMemcpyAsync(status.data(), Td.e, (size_t)nf * 4, cudaMemcpyDeviceToHost, st);
+                if (ce == cudaSuccess) ce = cudaMemcpyAsync(osz.data(), Td.c, (size_t)nf * 8, cudaMemcpyDeviceToHost, st);
+                if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+            }
+            if (rc != ZMT_ST_OK || ce != cudaSuccess) { cudaGetLastError(); c->lib_errcode = ZMT_ST_CUDA; return E.library; }
+            for (uint32_t i = 0; i < nf; i++) {
+                if (status[i] != ZMT_ST_OK) { c->lib_errcode = status[i]; return (status[i] == ZMT_ST_TRUNCATED || status[i] == ZMT_ST_TRAILING) ? E.frame_decompress : E.library; }
+                // frame by frame, in pieces of at most `piece` bytes (st_decompress writes as it goes)
+                uint64_t o = 0;
+                while (o < osz[i]) {
+                    GenBuffer b; b.buf = out.data() + ooff[i] + o; b.size = (size_t)((osz[i] - o) < piece ? (osz[i] - o) : piece); b.allocated = b.size;
+                    const size_t want = b.size;
+                    const int rv = rw->fn_write(rw->arg_write, &b);
+                    if (rv != 0) return mt_error(E, rv);
+                    c->outsize += b.size; o += want;
+                }
+            }
+            // drop what has been decoded
+            in.erase(in.begin() + 12, in.begin() + 12 + (long)pos);
+            pos = 0;
+        }
+        if (need_more) {
+            // ---- read ahead: at least one more piece, up to a batch beyond the parse position
+            size_t goal = in.size() + piece;
+            if (goal < 12 + pos + kPlainBatch) goal = 12 + pos + kPlainBatch;
+            if (in.size() - 12 - pos >= kPlainBatch) goal = in.size() + (in.size() - 12 - pos) / 2;     // one frame larger than a batch: read ahead geometrically
+            while (!eof && in.size() < goal) {
+                const size_t old = in.size();
+                in.resize(old + piece);
+                size_t got = 0;
+                const size_t e = read_some(E, rw, in.data() + old, piece, &got);
+                in.resize(old + got);
+                if (e) return e;
+                c->insize += got;
+                if (got == 0) eof = true;
+            }
+        } else if (eof && pos >= in.size() - 12) break;
     }
     return 0;
 }
@@ -784,7 +822,7 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
                 }
                 T = tables_at(s->h_tab, s->tab_cap);
                 T.a[0] = 0; T.d[0] = (uint32_t)toRead; T.b[0] = 0;
-                if (is_zstd) { T.g[0] = 0; T.f[0] = osz; T.d[0] = nsq; }
+                if (is_zstd) { T.g[0] = 0; T.f[0] = (nsq & 4u) ? ~0ull : osz; T.d[0] = nsq; }      // flag 4: no content size in the header, osz is a bound
                 in_used = fr.size(); out_used = osz; n = 1;
                 return true;
             };
@@ -851,7 +889,7 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
                     continue;
                 }
                 T.a[n] = in_used; T.d[n] = (uint32_t)toRead; T.b[n] = out_used;
-                if (is_zstd) { T.g[n] = nblk; T.f[n] = osz; T.d[n] = nsq; nblk = nblk_new; scr = scr_new; }     // T.d doubles as the per-frame "needs sequential pass" flag
+                if (is_zstd) { T.g[n] = nblk; T.f[n] = (nsq & 4u) ? ~0ull : osz; T.d[n] = nsq; nblk = nblk_new; scr = scr_new; }     // T.d = frame flags (sequential pass, checksum, no size)
                 in_used += 12 + toRead; out_used += osz; n++;
             }
             if (failed) break;

@@ -319,21 +319,67 @@ lz4_parse_blocks_kernel(const uint8_t* __restrict__ in, const uint8_t* __restric
 }
 
 // ---------------------------------------------------------------- pass B: match execution
+// Ticket order.  Blocks of a linked-block frame form a dependency chain (the first matches of a block usually read the
+// tail of the previous one), so tickets must not put the blocks of one frame on neighbouring warps: within a window of
+// LZX_WIN frames the order is block-index-major — block 0 of every frame of the window, then block 1 of every frame, ... —
+// which keeps as many independent chains in flight as there are frames in the window, and by the time block b+1 of a
+// frame comes up its block b has long finished.  (f, b-1) still always holds a lower ticket than (f, b): no deadlock.
+// A window whose frames have very different block counts would mostly hand out empty tickets; it falls back to
+// frame-major order (flag in the top bit of its base).
+#define LZX_WIN 16384u
+__global__ void __launch_bounds__(256)
+lz4_ticket_windows_kernel(const uint64_t* __restrict__ first_slot, uint32_t nframes, unsigned long long* __restrict__ wbase)
+{
+    __shared__ uint32_t red[256];
+    const uint32_t nwin = (nframes + LZX_WIN - 1) / LZX_WIN;
+    unsigned long long base = 0;
+    for (uint32_t w = 0; w < nwin; w++) {
+        const uint32_t f0 = w * LZX_WIN, f1 = f0 + LZX_WIN < nframes ? f0 + LZX_WIN : nframes;
+        uint32_t mx = 0;
+        for (uint32_t f = f0 + threadIdx.x; f < f1; f += 256) { const uint32_t c = (uint32_t)(first_slot[f + 1] - first_slot[f]); mx = c > mx ? c : mx; }
+        red[threadIdx.x] = mx;
+        __syncthreads();
+        for (uint32_t d = 128; d > 0; d >>= 1) { if (threadIdx.x < d && red[threadIdx.x + d] > red[threadIdx.x]) red[threadIdx.x] = red[threadIdx.x + d]; __syncthreads(); }
+        mx = red[0];
+        __syncthreads();
+        const unsigned long long real = first_slot[f1] - first_slot[f0], grid = (unsigned long long)(f1 - f0) * mx;
+        const bool frame_major = grid > 8 * real + 65536;
+        if (threadIdx.x == 0) wbase[w] = base | (frame_major ? (1ull << 63) : 0ull);
+        base += frame_major ? real : grid;
+    }
+    if (threadIdx.x == 0) wbase[nwin] = base;
+}
+
 __global__ void __launch_bounds__(32 * LZD_WARPS)
 lz4_exec_blocks_kernel(uint8_t* __restrict__ out, const uint64_t* __restrict__ out_off, const uint64_t* __restrict__ frame_off,
                        const uint64_t* __restrict__ first_slot, const LzBlk* __restrict__ tab, const unsigned long long* __restrict__ rec,
                        uint32_t* __restrict__ prog, const uint32_t* __restrict__ status, const uint32_t* __restrict__ needs_seq,
-                       unsigned int* __restrict__ ticket, uint32_t nframes, uint32_t slot_cap)
+                       unsigned long long* __restrict__ ticket, const unsigned long long* __restrict__ wbase, uint32_t nframes, uint32_t slot_cap)
 {
     const uint32_t lane = threadIdx.x & 31;
-    uint64_t nslots = first_slot[nframes];
-    if (nslots > slot_cap) nslots = slot_cap;
+    if (first_slot[nframes] > slot_cap) return;             // the scan reported the undersized table per frame
+    const uint32_t nwin = (nframes + LZX_WIN - 1) / LZX_WIN;
+    const unsigned long long ntickets = wbase[nwin] & ~(1ull << 63);
     volatile uint32_t* vprog = prog;
     for (;;) {
-        uint32_t t = 0;
-        if (lane == 0) t = atomicAdd(ticket, 1u);
-        t = __shfl_sync(ZMT_FULL_MASK, t, 0);
-        if (t >= nslots) break;
+        unsigned long long tk = 0;
+        if (lane == 0) tk = atomicAdd(ticket, 1ull);
+        tk = __shfl_sync(ZMT_FULL_MASK, tk, 0);
+        if (tk >= ntickets) break;
+        // ticket -> window (binary search over the window bases) -> (frame, block) -> slot
+        uint32_t lo = 0, hi = nwin;
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if ((wbase[mid] & ~(1ull << 63)) <= tk) lo = mid; else hi = mid; }
+        const unsigned long long wb = wbase[lo];
+        const unsigned long long tl = tk - (wb & ~(1ull << 63));
+        const uint32_t f0 = lo * LZX_WIN, wn = (f0 + LZX_WIN < nframes ? LZX_WIN : nframes - f0);
+        uint64_t t;
+        if (wb >> 63) t = first_slot[f0] + tl;                          // frame-major window
+        else {
+            const uint32_t fb = (uint32_t)(tl / wn), ff = f0 + (uint32_t)(tl % wn);
+            const uint64_t s0 = first_slot[ff];
+            if (fb >= first_slot[ff + 1] - s0) continue;                // this frame has fewer blocks
+            t = s0 + fb;
+        }
         const LzBlk B = tab[t];
         if (B.csize == 0) continue;                         // empty slot: nobody waits on it
         const uint32_t f = B.frame;

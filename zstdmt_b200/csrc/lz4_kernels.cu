@@ -1008,7 +1008,7 @@ static inline uint64_t a256(uint64_t x) { return (x + 255) & ~255ull; }
 // workspace: stored[] | computed[] | needs_seq[] | ticket | slot counts | first_slot | block table | progress | match records
 extern "C" size_t zmt_lz4d_workspace_bytes(uint32_t nframes, uint32_t nslots, uint64_t in_bytes)
 {
-    uint64_t sz = 3 * a256((uint64_t)nframes * 4) + 256 + 2 * a256(((uint64_t)nframes + 1) * 8);
+    uint64_t sz = 3 * a256((uint64_t)nframes * 4) + 256 + 2 * a256(((uint64_t)nframes + 1) * 8) + a256(((uint64_t)nframes / LZX_WIN + 2) * 8);
     sz += a256((uint64_t)nslots * sizeof(LzBlk)) + a256((uint64_t)nslots * 4);
     sz += a256((in_bytes / 3 + 8) * 8);
     return (size_t)sz + 1024;
@@ -1025,7 +1025,8 @@ extern "C" int zmt_lz4_decompress_device(const void* d_in, uint64_t in_bytes, co
     uint32_t* stored = (uint32_t*)w; w += a256((uint64_t)nframes * 4);
     uint32_t* computed = (uint32_t*)w; w += a256((uint64_t)nframes * 4);
     uint32_t* needs_seq = (uint32_t*)w; w += a256((uint64_t)nframes * 4);
-    unsigned int* ticket = (unsigned int*)w; w += 256;
+    unsigned long long* ticket = (unsigned long long*)w; w += 256;
+    unsigned long long* wbase = (unsigned long long*)w; w += a256(((uint64_t)nframes / LZX_WIN + 2) * 8);
     uint64_t* slot_cnt = (uint64_t*)w; w += a256(((uint64_t)nframes + 1) * 8);
     uint64_t* first_slot = (uint64_t*)w; w += a256(((uint64_t)nframes + 1) * 8);
     LzBlk* tab = (LzBlk*)w; w += a256((uint64_t)nslots * sizeof(LzBlk));
@@ -1037,6 +1038,7 @@ extern "C" int zmt_lz4_decompress_device(const void* d_in, uint64_t in_bytes, co
     const uint8_t* in = (const uint8_t*)d_in;
     lz4_slot_counts_kernel<<<(nframes + 255) / 256, 256, 0, stream>>>(d_out_off, nframes, slot_cnt);
     scan_u64_kernel<<<1, 1024, 0, stream>>>(slot_cnt, first_slot, nframes);
+    lz4_ticket_windows_kernel<<<1, 256, 0, stream>>>(first_slot, nframes, wbase);
     lz4_scan_frames_kernel<<<(nframes + 127) / 128, 128, 0, stream>>>(in, d_frame_off, d_frame_csize, d_out_off, first_slot, nslots, tab, prog, d_status, stored, needs_seq, nframes);
     zmt_dbg_check(stream, "lz4_scan_frames_kernel");
     { ZmtProfScope ps(ZMT_K_LZ4_DECODE, stream);
@@ -1048,7 +1050,7 @@ extern "C" int zmt_lz4_decompress_device(const void* d_in, uint64_t in_bytes, co
         const uint32_t need = (nslots + LZD_WARPS - 1) / LZD_WARPS;
         ZmtProfScope ps(ZMT_K_LZ4_DEXEC, stream);
         lz4_exec_blocks_kernel<<<need < maxg ? need : maxg, 32 * LZD_WARPS, 0, stream>>>(
-            (uint8_t*)d_out, d_out_off, d_frame_off, first_slot, tab, rec, prog, d_status, needs_seq, ticket, nframes, nslots);
+            (uint8_t*)d_out, d_out_off, d_frame_off, first_slot, tab, rec, prog, d_status, needs_seq, ticket, wbase, nframes, nslots);
     }
     zmt_dbg_check(stream, "lz4_exec_blocks_kernel");
     lz4_decode_frames_seq_kernel<<<(nframes + LZD_WARPS - 1) / LZD_WARPS, 32 * LZD_WARPS, 0, stream>>>(

@@ -45,6 +45,11 @@ struct ZBlk {
 };
 struct ZDSeq { uint32_t ll; uint32_t off; uint32_t ml; uint32_t pad; };
 
+// per-frame flags (the d_frame_seq[] argument; produced by zmt_zstd_scan_frame_host)
+#define ZF_NEEDS_SEQ 1u     // blocks depend on earlier blocks: frame-sequential entropy pass
+#define ZF_CHECKSUM  2u     // 4-byte content checksum (low 32 bits of XXH64) follows the last block
+#define ZF_NO_SIZE   4u     // no Frame_Content_Size: the reported size is an upper bound (128 KiB per compressed block)
+
 // ---------------------------------------------------------------- predefined FSE decode tables
 struct ZFseDTable { uint8_t sym[64]; uint8_t nb[64]; uint16_t base[64]; uint32_t log; };
 __constant__ ZFseDTable d_fse_ll, d_fse_of, d_fse_ml;
@@ -405,7 +410,7 @@ zstd_entropy_kernel(const uint8_t* __restrict__ in, const ZBlk* __restrict__ blo
     if (b >= nblocks) return;
     const ZBlk B = blocks[b];
     if (B.type != ZB_CMP) { if (lane == 0) regen[b] = B.regen_hint; return; }
-    if (frame_seq[B.frame]) return;                          // this frame goes through the frame-sequential pass
+    if (frame_seq[B.frame] & ZF_NEEDS_SEQ) return;           // this frame goes through the frame-sequential pass
     ZWarpTabs& W = tabs[wid];
     zd_load_predef(W, lane);
     uint32_t rg = 0;
@@ -431,7 +436,7 @@ zstd_entropy_seq_kernel(const uint8_t* __restrict__ in, const ZBlk* __restrict__
     if (f >= nframes) return;
     const uint32_t st0 = status[f];
     const bool flagged = (st0 & 0x8000u) != 0;
-    if (!frame_seq[f] && !flagged) return;
+    if (!(frame_seq[f] & ZF_NEEDS_SEQ) && !flagged) return;
     __syncwarp();
     if (lane == 0 && flagged) status[f] = 0;
     ZWarpTabs& W = tabs[wid];
@@ -462,19 +467,19 @@ __global__ void zstd_offsets_kernel(const ZBlk* __restrict__ blocks, uint32_t nb
     const uint64_t cap = out_off[f + 1] - out_off[f];
     for (uint32_t b = b0; b < b1; b++) { blk_out[b] = out_off[f] + pos; pos += regen[b]; }
     out_size[f] = pos;
-    if ((status[f] & 0xFF) == 0 && (pos != expect[f] || pos > cap)) status[f] = pos > cap ? ZMT_ST_DST_SMALL : ZMT_ST_CONTENT_SIZE;
+    // expect = ~0: the frame header carries no content size (streamed frames); the room then is only a bound
+    if ((status[f] & 0xFF) == 0 && ((expect[f] != ~0ull && pos != expect[f]) || pos > cap)) status[f] = pos > cap ? ZMT_ST_DST_SMALL : ZMT_ST_CONTENT_SIZE;
 }
 
 // ---------------------------------------------------------------- kernel 3: sequence execution
 #define ZX_WARPS 8
-__global__ void __launch_bounds__(32 * ZX_WARPS)
-zstd_execute_kernel(const uint8_t* __restrict__ in, const ZBlk* __restrict__ blocks, uint32_t nblocks, const uint8_t* __restrict__ scratch,
-                    const uint32_t* __restrict__ regen, const uint64_t* __restrict__ blk_out, const uint64_t* __restrict__ out_off,
-                    uint8_t* __restrict__ out, uint32_t* __restrict__ done, uint32_t* __restrict__ status)
+// One block, one warp.  Blocks are handed out by a ticket counter (see the kernel below), so every block this one may wait
+// for — lower indices of the same frame — is held by a warp that is already running: the wait cannot deadlock whatever
+// order the hardware schedules CTAs in.
+__device__ void zx_block(uint32_t b, uint32_t lane, const uint8_t* __restrict__ in, const ZBlk* __restrict__ blocks, const uint8_t* __restrict__ scratch,
+                         const uint32_t* __restrict__ regen, const uint64_t* __restrict__ blk_out, const uint64_t* __restrict__ out_off,
+                         uint8_t* __restrict__ out, uint32_t* __restrict__ done, uint32_t* __restrict__ status)
 {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t b = blockIdx.x * ZX_WARPS + (threadIdx.x >> 5);
-    if (b >= nblocks) return;
     const ZBlk B = blocks[b];
     volatile uint32_t* vdone = done;
     // a frame that already failed: do not touch memory, just release the waiters
@@ -553,6 +558,89 @@ zstd_execute_kernel(const uint8_t* __restrict__ in, const ZBlk* __restrict__ blo
     if (lane == 0) { __threadfence(); vdone[b] = 1; }
 }
 
+__global__ void __launch_bounds__(32 * ZX_WARPS)
+zstd_execute_kernel(const uint8_t* __restrict__ in, const ZBlk* __restrict__ blocks, uint32_t nblocks, const uint8_t* __restrict__ scratch,
+                    const uint32_t* __restrict__ regen, const uint64_t* __restrict__ blk_out, const uint64_t* __restrict__ out_off,
+                    uint8_t* __restrict__ out, uint32_t* __restrict__ done, uint32_t* __restrict__ status, unsigned int* __restrict__ ticket)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    for (;;) {
+        uint32_t b = 0;
+        if (lane == 0) b = atomicAdd(ticket, 1u);
+        b = __shfl_sync(0xFFFFFFFFu, b, 0);
+        if (b >= nblocks) return;
+        zx_block(b, lane, in, blocks, scratch, regen, blk_out, out_off, out, done, status);
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------- kernel 4: frame content checksum (XXH64, seed 0; RFC 8878 3.1.1)
+// One warp per frame that carries a checksum (what the stock zstd CLI writes by default; the reference path —
+// ZSTD_compress, zstd-mt_compress.c:284-286 — never does).  Lanes 0..3 run the four accumulator chains, each over its
+// 8-byte word of every 32-byte stripe; eight stripes are loaded ahead of their use.
+#define XP64_1 0x9E3779B185EBCA87ull
+#define XP64_2 0xC2B2AE3D27D4EB4Full
+#define XP64_3 0x165667B19E3779F9ull
+#define XP64_4 0x85EBCA77C2B2AE63ull
+#define XP64_5 0x27D4EB2F165667C5ull
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+__device__ __forceinline__ uint64_t xxh64_round(uint64_t acc, uint64_t v) { return rotl64(acc + v * XP64_2, 31) * XP64_1; }
+__device__ __forceinline__ uint64_t xxh64_merge(uint64_t h, uint64_t v) { return (h ^ xxh64_round(0, v)) * XP64_1 + XP64_4; }
+__device__ __forceinline__ uint64_t ldg_le64u(const uint8_t* p)
+{
+    if (((uintptr_t)p & 7) == 0) return *reinterpret_cast<const uint64_t*>(p);
+    uint64_t v = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) v |= (uint64_t)p[i] << (8 * i);
+    return v;
+}
+
+__global__ void __launch_bounds__(32 * ZD_WARPS)
+zstd_checksum_kernel(const uint8_t* __restrict__ in, const ZBlk* __restrict__ blocks, const uint32_t* __restrict__ frame_first_blk,
+                     const uint32_t* __restrict__ frame_seq, const uint8_t* __restrict__ out, const uint64_t* __restrict__ out_off,
+                     const unsigned long long* __restrict__ out_size, uint32_t* __restrict__ status, uint32_t nframes)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t f = blockIdx.x * ZD_WARPS + (threadIdx.x >> 5);
+    if (f >= nframes || !(frame_seq[f] & ZF_CHECKSUM) || (status[f] & 0xFF) != 0) return;
+    const uint32_t b1 = frame_first_blk[f + 1];
+    if (b1 == frame_first_blk[f]) return;
+    const ZBlk BL = blocks[b1 - 1];
+    const uint8_t* p = out + out_off[f];
+    const uint64_t n = out_size[f];
+    uint64_t h;
+    if (n >= 32) {
+        const uint32_t j = lane & 3;
+        uint64_t acc = j == 0 ? XP64_1 + XP64_2 : j == 1 ? XP64_2 : j == 2 ? 0ull : 0ull - XP64_1;
+        const uint64_t ns = n >> 5;
+        uint64_t s = 0;
+        if (lane < 4) {
+            for (; s + 8 <= ns; s += 8) {
+                uint64_t v[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) v[k] = ldg_le64u(p + ((s + k) << 5) + 8 * j);
+#pragma unroll
+                for (int k = 0; k < 8; k++) acc = xxh64_round(acc, v[k]);
+            }
+            for (; s < ns; s++) acc = xxh64_round(acc, ldg_le64u(p + (s << 5) + 8 * j));
+        }
+        const uint64_t a1 = __shfl_sync(0xFFFFFFFFu, acc, 0), a2 = __shfl_sync(0xFFFFFFFFu, acc, 1), a3 = __shfl_sync(0xFFFFFFFFu, acc, 2), a4 = __shfl_sync(0xFFFFFFFFu, acc, 3);
+        h = rotl64(a1, 1) + rotl64(a2, 7) + rotl64(a3, 12) + rotl64(a4, 18);
+        h = xxh64_merge(h, a1); h = xxh64_merge(h, a2); h = xxh64_merge(h, a3); h = xxh64_merge(h, a4);
+    } else h = XP64_5;
+    if (lane == 0) {
+        h += n;
+        const uint8_t* q = p + (n & ~31ull); const uint8_t* end = p + n;
+        while (q + 8 <= end) { h ^= xxh64_round(0, ldg_le64u(q)); h = rotl64(h, 27) * XP64_1 + XP64_4; q += 8; }
+        if (q + 4 <= end) { h ^= (uint64_t)((uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24)) * XP64_1; h = rotl64(h, 23) * XP64_2 + XP64_3; q += 4; }
+        while (q < end) { h ^= (*q) * XP64_5; h = rotl64(h, 11) * XP64_1; q++; }
+        h ^= h >> 33; h *= XP64_2; h ^= h >> 29; h *= XP64_3; h ^= h >> 32;
+        const uint8_t* c = in + BL.comp_off + BL.comp_size;
+        const uint32_t stored = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) | ((uint32_t)c[3] << 24);
+        if (stored != (uint32_t)h) zd_fail(status, f, ZMT_ST_CONTENT_CHECKSUM);
+    }
+}
+
 // ================================================================ host side
 static void zd_build_dtable(ZFseDTable& T, const int16_t* norm, int nsym, int log)
 {
@@ -568,6 +656,16 @@ static void zd_build_dtable(ZFseDTable& T, const int16_t* norm, int nsym, int lo
         T.nb[i] = (uint8_t)(log - hb);
         T.base[i] = (uint16_t)(((uint32_t)x << T.nb[i]) - size);
     }
+}
+
+static int zd_sm_count()
+{
+    static std::mutex mu; static int n[64];
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 148;
+    std::lock_guard<std::mutex> g(mu);
+    if (!n[dev]) { cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev); if (n[dev] <= 0) n[dev] = 148; }
+    return n[dev];
 }
 
 static int zd_tables_init()
@@ -617,19 +715,22 @@ extern "C" int zmt_zstd_scan_frame_host2(const uint8_t* frame, size_t n, uint64_
 {
     *needs_seq = 0;
     ZBlk* out = (ZBlk*)blocks_out;
-    if (n < 6 || h_rd32(frame) != 0xFD2FB528u) return ZMT_ST_BAD_MAGIC;
+    if (n < 6 || h_rd32(frame) != 0xFD2FB528u) return n < 6 ? ZMT_ST_TRUNCATED : ZMT_ST_BAD_MAGIC;
     const uint32_t fhd = frame[4], fcs = fhd >> 6, single = (fhd >> 5) & 1, did = fhd & 3;
     if (fhd & 0x08) return ZMT_ST_BAD_HEADER;
-    if (fhd & 0x04) return ZMT_ST_UNSUPPORTED;                       // content checksum (XXH64) not produced by the reference path
-    size_t pos = 5 + (single ? 0 : 1) + (did == 0 ? 0 : did == 1 ? 1 : did == 2 ? 2 : 4);
+    const bool has_chk = (fhd & 0x04) != 0;                          // XXH64 content checksum after the last block (verified on the device)
+    if (did) return ZMT_ST_UNSUPPORTED;                               // dictionaries: not on the reference path
+    size_t pos = 5 + (single ? 0 : 1);
     const size_t fl = fcs == 0 ? (single ? 1 : 0) : fcs == 1 ? 2 : fcs == 2 ? 4 : 8;
-    if (fl == 0) return ZMT_ST_UNSUPPORTED;                           // unknown content size: the reference path always has it
     if (n < pos + fl) return ZMT_ST_TRUNCATED;
-    uint64_t cs;
+    uint64_t cs = 0;
     if (fl == 1) cs = frame[pos]; else if (fl == 2) cs = (uint64_t)(frame[pos] | (frame[pos + 1] << 8)) + 256;
-    else if (fl == 4) cs = h_rd32(frame + pos); else cs = (uint64_t)h_rd32(frame + pos) | ((uint64_t)h_rd32(frame + pos + 4) << 32);
+    else if (fl == 4) cs = h_rd32(frame + pos); else if (fl == 8) cs = (uint64_t)h_rd32(frame + pos) | ((uint64_t)h_rd32(frame + pos + 4) << 32);
     pos += fl;
-    *content_size = cs;
+    const bool no_size = fl == 0;                                     // streamed frame: size from the blocks (bound: 128 KiB per compressed block)
+    uint64_t bound = 0;
+    if (has_chk) *needs_seq |= ZF_CHECKSUM;
+    if (no_size) *needs_seq |= ZF_NO_SIZE;
     bool first = true;
     for (;;) {
         if (n - pos < 3) return ZMT_ST_TRUNCATED;
@@ -640,6 +741,7 @@ extern "C" int zmt_zstd_scan_frame_host2(const uint8_t* frame, size_t n, uint64_
         ZBlk& B = out[*nblocks_io];
         memset(&B, 0, sizeof(B));
         B.frame = frame_idx; B.type = type; B.first = first ? 1 : 0; B.comp_off = base_off + pos;
+        bound += type == ZB_CMP ? 128 * 1024 : bs;
         if (type == ZB_RAW) { if (n - pos < bs) return ZMT_ST_TRUNCATED; B.comp_size = bs; B.regen_hint = bs; pos += bs; }
         else if (type == ZB_RLE) { if (n - pos < 1) return ZMT_ST_TRUNCATED; B.comp_size = 1; B.regen_hint = bs; pos += 1; }
         else {
@@ -668,8 +770,8 @@ extern "C" int zmt_zstd_scan_frame_host2(const uint8_t* frame, size_t n, uint64_
             // any non-predefined sequence table mode may be followed by Repeat_Mode -> frame-sequential pass
             {
                 const uint32_t used = q0 == 0 ? 1u : q0 < 128 ? 1u : q0 < 255 ? 2u : 3u;
-                if (lt == 3) *needs_seq = 1;
-                if (nseq && qn > used && q[used] != 0) *needs_seq = 1;
+                if (lt == 3) *needs_seq |= ZF_NEEDS_SEQ;
+                if (nseq && qn > used && q[used] != 0) *needs_seq |= ZF_NEEDS_SEQ;
             }
             B.comp_size = bs; B.regen_hint = lregen; B.nseq = nseq;
             B.seq_off = *scratch_used; *scratch_used += (((uint64_t)nseq * sizeof(ZDSeq)) + 15) & ~15ull;
@@ -680,6 +782,8 @@ extern "C" int zmt_zstd_scan_frame_host2(const uint8_t* frame, size_t n, uint64_
         first = false;
         if (last) break;
     }
+    if (has_chk) { if (n - pos < 4) return ZMT_ST_TRUNCATED; pos += 4; }
+    *content_size = no_size ? bound : cs;
     if (consumed) { *consumed = pos; return ZMT_ST_OK; }
     return pos == n ? ZMT_ST_OK : ZMT_ST_TRAILING;
 }
@@ -690,7 +794,7 @@ extern "C" size_t zmt_zstd_blk_desc_bytes(void) { return sizeof(ZBlk); }
 extern "C" size_t zmt_zstdd_workspace_bytes(uint32_t nframes, uint32_t nblocks, uint64_t scratch_bytes)
 {
     return (size_t)(((uint64_t)nblocks * 4 + 255) & ~255ull) * 2 + (((uint64_t)nblocks * 8 + 255) & ~255ull) + (((uint64_t)nframes * 8 + 255) & ~255ull)
-           + scratch_bytes + 1024;
+           + 256 + scratch_bytes + 1024;
 }
 
 // d_blocks: nblocks descriptors (device copy of what zmt_zstd_scan_frame_host produced); d_frame_first_blk: nframes+1;
@@ -707,6 +811,7 @@ extern "C" int zmt_zstd_decompress_device(const void* d_in, const void* d_blocks
     uint32_t* done = (uint32_t*)w; w += (((uint64_t)nblocks * 4 + 255) & ~255ull);
     uint64_t* blk_out = (uint64_t*)w; w += (((uint64_t)nblocks * 8 + 255) & ~255ull);
     w += (((uint64_t)nframes * 8 + 255) & ~255ull);
+    unsigned int* xticket = (unsigned int*)w; w += 256;
     uint8_t* scratch = w;
     cudaMemsetAsync(d_status, 0, (size_t)nframes * 4, stream);
     cudaMemsetAsync(regen, 0, (size_t)nblocks * 4, stream);
@@ -720,8 +825,13 @@ extern "C" int zmt_zstd_decompress_device(const void* d_in, const void* d_blocks
     zstd_offsets_kernel<<<(nframes + 127) / 128, 128, 0, stream>>>((const ZBlk*)d_blocks, nblocks, d_frame_first_blk, regen, blk_out, d_out_off, d_expect,
                                                                    (unsigned long long*)d_out_size, d_status, nframes);
     if (nblocks) {
-        zstd_execute_kernel<<<(nblocks + ZX_WARPS - 1) / ZX_WARPS, 32 * ZX_WARPS, 0, stream>>>((const uint8_t*)d_in, (const ZBlk*)d_blocks, nblocks, scratch, regen, blk_out,
-                                                                                           d_out_off, (uint8_t*)d_out, done, d_status);
+        const uint32_t gmax = (uint32_t)(zd_sm_count() * (2048 / (32 * ZX_WARPS)));
+        const uint32_t gneed = (nblocks + ZX_WARPS - 1) / ZX_WARPS;
+        cudaMemsetAsync(xticket, 0, 4, stream);
+        zstd_execute_kernel<<<gneed < gmax ? gneed : gmax, 32 * ZX_WARPS, 0, stream>>>((const uint8_t*)d_in, (const ZBlk*)d_blocks, nblocks, scratch, regen, blk_out,
+                                                                                     d_out_off, (uint8_t*)d_out, done, d_status, xticket);
+        zstd_checksum_kernel<<<(nframes + ZD_WARPS - 1) / ZD_WARPS, 32 * ZD_WARPS, 0, stream>>>((const uint8_t*)d_in, (const ZBlk*)d_blocks, d_frame_first_blk, d_frame_seq,
+                                                                                           (const uint8_t*)d_out, d_out_off, (const unsigned long long*)d_out_size, d_status, nframes);
     }
     zmt_prof_mark(ZMT_K_ZSTD_DECODE, stream, 1);
     return cudaGetLastError() == cudaSuccess ? ZMT_ST_OK : ZMT_ST_CUDA;

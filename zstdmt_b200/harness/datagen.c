@@ -190,7 +190,8 @@ void zmt_gen_chunk(int kind, uint64_t chunk_index, uint8_t* buf, size_t n)
     }
 }
 
-typedef struct { int kind; uint64_t first, count, stride; size_t chunk; uint8_t* buf; size_t total; uint64_t next; pthread_mutex_t mu; } gen_job;
+typedef struct { int kind; uint64_t first, count, stride; size_t chunk; uint8_t* buf; size_t total; uint64_t next; pthread_mutex_t mu;
+                 uint64_t batch, rank, world; } gen_job;
 
 static void* gen_worker(void* arg)
 {
@@ -201,7 +202,10 @@ static void* gen_worker(void* arg)
         if (i >= j->count) break;
         {
             size_t off = (size_t)i * j->chunk, n = j->total - off < j->chunk ? j->total - off : j->chunk;
-            zmt_gen_chunk(j->kind, j->first + i * j->stride, j->buf + off, n);
+            /* batch != 0: chunks dealt to `world` consumers in batches (the product's granularity): local chunk i of
+             * consumer `rank` is global chunk (i / batch) * batch * world + rank * batch + i % batch */
+            const uint64_t g = j->batch ? (i / j->batch) * j->batch * j->world + j->rank * j->batch + i % j->batch : j->first + i * j->stride;
+            zmt_gen_chunk(j->kind, g, j->buf + off, n);
         }
     }
     return NULL;
@@ -209,10 +213,24 @@ static void* gen_worker(void* arg)
 
 /* Fill `total` bytes = consecutive chunks of `chunk` bytes; local chunk i gets global index
  * first + i*stride (stride = world size for the round-robin multi-GPU split). */
+static void gen_run(int kind, uint64_t first, uint64_t stride, uint64_t batch, uint64_t rank, uint64_t world, size_t chunk, uint8_t* buf, size_t total, int nthreads);
+
 void zmt_gen_stream(int kind, uint64_t first, uint64_t stride, size_t chunk, uint8_t* buf, size_t total, int nthreads)
+{
+    gen_run(kind, first, stride, 0, 0, 1, chunk, buf, total, nthreads);
+}
+
+/* the share of consumer `rank` of `world` when the global stream is dealt round-robin in batches of `batch` chunks */
+void zmt_gen_stream_dealt(int kind, uint64_t rank, uint64_t world, uint64_t batch, size_t chunk, uint8_t* buf, size_t total, int nthreads)
+{
+    gen_run(kind, 0, 1, batch ? batch : 1, rank, world ? world : 1, chunk, buf, total, nthreads);
+}
+
+static void gen_run(int kind, uint64_t first, uint64_t stride, uint64_t batch, uint64_t rank, uint64_t world, size_t chunk, uint8_t* buf, size_t total, int nthreads)
 {
     gen_job j; pthread_t th[64]; int t;
     if (!total || !chunk) return;
+    j.batch = batch; j.rank = rank; j.world = world;
     j.kind = kind; j.first = first; j.stride = stride ? stride : 1; j.chunk = chunk; j.buf = buf; j.total = total; j.next = 0;
     j.count = (total + chunk - 1) / chunk;
     pthread_mutex_init(&j.mu, NULL);
