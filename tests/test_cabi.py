@@ -160,3 +160,20 @@ def test_zstd_host_scan_flags_checksum_and_missing_content_size():
         assert cs.value == src.size if exact else cs.value >= src.size
         nb2 = ctypes.c_uint32(0); s2 = ctypes.c_uint64(0)
         assert L.zmt_zstd_scan_frame_host(fr.ctypes.data, fr.size - 1, 0, 0, blocks.ctypes.data, ctypes.byref(nb2), cap, ctypes.byref(s2), ctypes.byref(cs), ctypes.byref(fl)) != 0
+
+
+def test_levels_above_the_implemented_class_are_announced_or_refused(monkeypatch, capfd):
+    """Levels the device encoder does not implement are accepted with a one-time notice (the CLI default for lz4 is 3),
+    or refused like any bad parameter under ZSTDMT_B200_STRICT_LEVEL=1 — never silently mapped."""
+    L = z.lib()
+    c = L.LZ4MT_createCCtx(2, 9, 1 << 20)
+    assert c
+    L.LZ4MT_freeCCtx(c)
+    err = capfd.readouterr().err
+    assert "level 9" in err and "level-2" in err
+    c = L.LZ4MT_createCCtx(2, 12, 1 << 20); assert c; L.LZ4MT_freeCCtx(c)
+    assert "level" not in capfd.readouterr().err                     # said once per codec
+    monkeypatch.setenv("ZSTDMT_B200_STRICT_LEVEL", "1")
+    assert not L.LZ4MT_createCCtx(2, 3, 1 << 20) and not L.ZSTDCB_createCCtx(2, 5, 0)
+    c = L.LZ4MT_createCCtx(2, 1, 1 << 20); assert c; L.LZ4MT_freeCCtx(c)
+    c = L.ZSTDCB_createCCtx(2, 3, 0); assert c; L.ZSTDCB_freeCCtx(c)

@@ -47,12 +47,16 @@ def build_product(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     if not os.path.exists(nvcc):
         nvcc = "nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs + ["-lpthread"]
+    tmp = LIB + ".tmp.%d" % os.getpid()         # link under a scratch name, then rename: readers never see a half-written library
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + srcs + ["-lpthread"]
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed building libzstdmt_b200.so")
+    os.replace(tmp, LIB)
     return LIB
 
 

@@ -999,6 +999,24 @@ Ctx* ctx_new(int codec, bool comp, int threads, int level, size_t inputsize)
 }
 void ctx_delete(Ctx* c) { if (!c) return; ctx_release_slots(c); delete c; }
 
+// Levels.  The device encoders implement one search class per codec (LZ4: the greedy single-probe parse of level 1-2;
+// zstd: the same parse + Huffman / predefined-FSE entropy stage, "level 3 (predefined FSE tables)" in BASELINE terms).
+// Higher levels are accepted — the CLI default for lz4 is 3 (programs/lz4-mt.c:19) and must keep working — and produce
+// the same stream; that is said once on stderr (ZSTDMT_B200_QUIET=1 silences it) instead of silently, and
+// ZSTDMT_B200_STRICT_LEVEL=1 turns it into the reference's own answer for a bad parameter (create returns NULL,
+// lib/lz4-mt_compress.c:103-108).
+bool level_ok(int codec, int level)
+{
+    const int implemented = codec == CODEC_LZ4 ? 2 : 3;
+    if (level <= implemented) return true;
+    if (getenv("ZSTDMT_B200_STRICT_LEVEL")) return false;
+    static std::atomic<int> told[3];
+    if (!getenv("ZSTDMT_B200_QUIET") && told[codec].exchange(1) == 0)
+        fprintf(stderr, "[zstdmt_b200] %s level %d requested: the device encoder implements the level-%d search class, the stream is valid but its ratio is that class's\n",
+                codec == CODEC_LZ4 ? "lz4" : "zstd", level, implemented);
+    return true;
+}
+
 const char* status_string(size_t st)
 {
     switch (st) {
@@ -1056,6 +1074,7 @@ void* LZ4MT_createCCtx(int threads, int level, int inputsize)                   
     if (threads < 1 || threads > 128) return nullptr;
     if (level < 1 || level > 12) return nullptr;
     if (inputsize < 0) return nullptr;
+    if (!level_ok(CODEC_LZ4, level)) return nullptr;
     return ctx_new(CODEC_LZ4, true, threads, level, inputsize ? (size_t)inputsize : (size_t)4 << 20);
 }
 size_t LZ4MT_compressCCtx(void* ctx, void* rdwr)                                       // lz4-mt_compress.c:312-353
@@ -1100,6 +1119,7 @@ void* ZSTDCB_createCCtx(int threads, int level, int inputsize)                  
     if (threads < 1 || threads > 128) return nullptr;
     if (level < 1 || level > 22) return nullptr;
     if (inputsize < 0) return nullptr;
+    if (!level_ok(CODEC_ZSTD, level)) return nullptr;
     size_t chunk = (size_t)inputsize;
     if (!chunk) {
         // the reference indexes its table by `level`, not level-1 (zstd-mt_compress.c:119-127); level 22 reads past

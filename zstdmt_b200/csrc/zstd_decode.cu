@@ -20,6 +20,7 @@
 // as ZMT_ST_UNSUPPORTED, never decoded on the CPU): dictionaries, frames without a content size, XXH64 checksums.
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <mutex>
 #include <vector>
@@ -42,7 +43,14 @@ struct ZBlk {
     uint32_t first;         // 1 if first block of its frame
     uint64_t seq_off;       // scratch offsets (bytes) for this block's sequence records / literals
     uint64_t lit_off;
+    // blocks whose tables come from an earlier block of the frame (treeless literals, Repeat_Mode sequence tables): index of
+    // the block whose section header DESCRIBES the table in use (ZB_SELF / ZB_PREDEF / ZB_NONE otherwise) — found by the
+    // host scan, so that every block can be entropy-decoded on its own
+    uint32_t huf_src, ll_src, of_src, ml_src;
 };
+#define ZB_SELF   0xFFFFFFFFu
+#define ZB_PREDEF 0xFFFFFFFEu
+#define ZB_NONE   0xFFFFFFFDu
 struct ZDSeq { uint32_t ll; uint32_t off; uint32_t ml; uint32_t pad; };
 
 // per-frame flags (the d_frame_seq[] argument; produced by zmt_zstd_scan_frame_host)
@@ -61,9 +69,10 @@ __constant__ uint8_t  d_ll_bits[36], d_ml_bits[53];
 // A 64-bit window of the stream (bits [wbit, wbit + 64)) lives in registers and is refilled with eight byte loads
 // when a read would fall below it — about once per 56 bits instead of four byte loads per read.
 struct BackBits {
-    const uint8_t* p; int32_t off; int32_t wbit; uint64_t win;
+    const uint8_t* p; int32_t off; int32_t wbit; int32_t nbytes; uint64_t win;
     __device__ __forceinline__ bool init(const uint8_t* s, uint32_t n)
     {
+        nbytes = (int32_t)n;
         if (n == 0) return false;
         const uint32_t lastb = s[n - 1];
         if (lastb == 0) return false;
@@ -81,8 +90,17 @@ struct BackBits {
             const int32_t tb = (top + 7) >> 3;           // window = the 8 bytes ending with the byte that holds bit top-1 (floor for negatives)
             const int32_t b0 = tb - 8;
             uint64_t w = 0;
+            if (b0 >= 0 && tb + 8 <= nbytes) {
+                // two aligned 8-byte loads + a funnel shift (the second word stays inside the stream: tb + 8 <= n)
+                const uint8_t* a = p + b0;
+                const uint64_t* A = reinterpret_cast<const uint64_t*>((uintptr_t)a & ~(uintptr_t)7);
+                const uint32_t sh = (uint32_t)((uintptr_t)a & 7) * 8;
+                const uint64_t x = A[0];
+                w = sh ? (x >> sh) | (A[1] << (64 - sh)) : x;
+            } else {
 #pragma unroll
-            for (int k = 0; k < 8; k++) { const int32_t b = b0 + k; if (b >= 0) w |= (uint64_t)p[b] << (8 * k); }
+                for (int k = 0; k < 8; k++) { const int32_t b = b0 + k; if (b >= 0) w |= (uint64_t)p[b] << (8 * k); }
+            }
             win = w; wbit = b0 * 8;
         }
         // bits above the stream end never matter: callers only ask for bits that exist or pad below the start
@@ -91,6 +109,26 @@ struct BackBits {
 };
 
 __device__ __forceinline__ void zd_fail(uint32_t* status, uint32_t f, uint32_t code) { atomicCAS(&status[f], 0u, code); }
+
+// literals section header of a compressed block -> header bytes, compressed size, type, size format; false if malformed
+__device__ __forceinline__ bool zd_lit_header(const uint8_t* src, uint32_t n, uint32_t* lhdr, uint32_t* lcomp, uint32_t* lregen, uint32_t* ltype, uint32_t* sf_out)
+{
+    if (n < 1) return false;
+    const uint32_t b0 = src[0], lt = b0 & 3, sf = (b0 >> 2) & 3;
+    *ltype = lt; *sf_out = sf;
+    if (lt < 2) {
+        if (sf == 0 || sf == 2) { *lregen = b0 >> 3; *lhdr = 1; }
+        else if (sf == 1) { if (n < 2) return false; *lregen = (b0 >> 4) | ((uint32_t)src[1] << 4); *lhdr = 2; }
+        else { if (n < 3) return false; *lregen = (b0 >> 4) | ((uint32_t)src[1] << 4) | ((uint32_t)src[2] << 12); *lhdr = 3; }
+        *lcomp = lt == 0 ? *lregen : 1;
+    } else {
+        if (n < 5) return false;
+        if (sf < 2) { const uint32_t v = src[0] | (src[1] << 8) | ((uint32_t)src[2] << 16); *lregen = (v >> 4) & 0x3FF; *lcomp = (v >> 14) & 0x3FF; *lhdr = 3; }
+        else if (sf == 2) { const uint32_t v = ldg_le32(src); *lregen = (v >> 4) & 0x3FFF; *lcomp = (v >> 18) & 0x3FFF; *lhdr = 4; }
+        else { const uint64_t v = (uint64_t)ldg_le32(src) | ((uint64_t)src[4] << 32); *lregen = (uint32_t)((v >> 4) & 0x3FFFF); *lcomp = (uint32_t)((v >> 22) & 0x3FFFF); *lhdr = 5; }
+    }
+    return (uint64_t)*lhdr + *lcomp <= n;
+}
 
 // ---------------------------------------------------------------- per-warp decoding tables (shared memory)
 // FSE decode entry: base (16) | nbBits (8) << 16 | symbol << 24
@@ -181,34 +219,12 @@ __device__ bool zd_seq_table(ZTabRef& cur, uint32_t mode, uint32_t* custom, cons
     return true;                                           // repeat: keep cur
 }
 
-// Decode one compressed block with one warp.  `fs` (frame state) carries tables + repeat offsets across blocks in the
-// frame-sequential pass; in the block-parallel pass fs == nullptr and anything that needs earlier blocks returns
-// ZD_NEEDS_SEQ.  Returns 0 ok / ZMT_ST_* / ZD_NEEDS_SEQ; *regen_out = regenerated bytes.
-struct ZFrameState { ZTabRef ll, of, ml; uint32_t rep[3]; bool have_tabs; };
-__device__ uint32_t zd_block(ZWarpTabs& W, const uint8_t* __restrict__ src, uint32_t n, const ZBlk& B, uint8_t* __restrict__ lit,
-                             ZDSeq* __restrict__ seqs, ZFrameState* fs, uint32_t* regen_out, uint32_t lane)
+// Huffman decoding table from a tree description at lp (at most `avail` bytes): direct 4-bit weights, or weights coded
+// with a small FSE table.  Whole warp; returns 0 / ZMT_ST_BLOCK, *tbytes_out = bytes of the description.
+__device__ uint32_t zd_huf_build(ZWarpTabs& W, const uint8_t* __restrict__ lp, uint32_t lcomp, uint32_t lane, uint32_t* tbytes_out)
 {
-    // ---- literals section
-    if (n < 1) return ZMT_ST_BLOCK;
-    const uint32_t b0 = src[0], ltype = b0 & 3, sf = (b0 >> 2) & 3;
-    uint32_t lregen, lcomp = 0, lhdr, streams = 1;
-    if (ltype < 2) {
-        if (sf == 0 || sf == 2) { lregen = b0 >> 3; lhdr = 1; }
-        else if (sf == 1) { lregen = (b0 >> 4) | ((uint32_t)src[1] << 4); lhdr = 2; }
-        else { lregen = (b0 >> 4) | ((uint32_t)src[1] << 4) | ((uint32_t)src[2] << 12); lhdr = 3; }
-        lcomp = ltype == 0 ? lregen : 1;
-    } else {
-        if (sf < 2) { const uint32_t v = src[0] | (src[1] << 8) | ((uint32_t)src[2] << 16); lregen = (v >> 4) & 0x3FF; lcomp = (v >> 14) & 0x3FF; lhdr = 3; streams = sf == 0 ? 1 : 4; }
-        else if (sf == 2) { const uint32_t v = ldg_le32(src); lregen = (v >> 4) & 0x3FFF; lcomp = (v >> 18) & 0x3FFF; lhdr = 4; streams = 4; }
-        else { const uint64_t v = (uint64_t)ldg_le32(src) | ((uint64_t)src[4] << 32); lregen = (uint32_t)((v >> 4) & 0x3FFFF); lcomp = (uint32_t)((v >> 22) & 0x3FFFF); lhdr = 5; streams = 4; }
-    }
-    if (lhdr + lcomp > n || lregen != B.regen_hint) return ZMT_ST_BLOCK;
-    const uint8_t* lp = src + lhdr;
-    if (ltype == 0) { for (uint32_t i = lane; i < lregen; i += 32) lit[i] = lp[i]; }
-    else if (ltype == 1) { const uint8_t v = lp[0]; for (uint32_t i = lane; i < lregen; i += 32) lit[i] = v; }
-    else {
-        uint32_t tbytes = 0;
-        if (ltype == 2) {
+    uint32_t tbytes = 0;
+    {
             // ---- Huffman tree description: direct 4-bit weights, or weights coded with a small FSE table
             const uint32_t hb = lp[0];
             uint32_t nw;
@@ -277,8 +293,44 @@ __device__ uint32_t zd_block(ZWarpTabs& W, const uint8_t* __restrict__ src, uint
             }
             if (lane == 0) W.hufbits = maxbits;
             __syncwarp();
+    }
+    *tbytes_out = tbytes;
+    return 0;
+}
+
+// Decode one compressed block with one warp.  `fs` (frame state) carries tables + repeat offsets across blocks in the
+// frame-sequential pass; in the block-parallel pass fs == nullptr and anything that needs earlier blocks returns
+// ZD_NEEDS_SEQ.  Returns 0 ok / ZMT_ST_* / ZD_NEEDS_SEQ; *regen_out = regenerated bytes.
+struct ZFrameState { ZTabRef ll, of, ml; uint32_t rep[3]; bool have_tabs; bool raw_offsets; bool huf_ready; };
+__device__ uint32_t zd_block(ZWarpTabs& W, const uint8_t* __restrict__ src, uint32_t n, const ZBlk& B, uint8_t* __restrict__ lit,
+                             ZDSeq* __restrict__ seqs, ZFrameState* fs, uint32_t* regen_out, uint32_t lane, uint32_t seq_done = 0, uint32_t seq_ml = 0,
+                             uint32_t lit_done = 0)
+{
+    // ---- literals section
+    if (n < 1) return ZMT_ST_BLOCK;
+    const uint32_t b0 = src[0], ltype = b0 & 3, sf = (b0 >> 2) & 3;
+    uint32_t lregen, lcomp = 0, lhdr, streams = 1;
+    if (ltype < 2) {
+        if (sf == 0 || sf == 2) { lregen = b0 >> 3; lhdr = 1; }
+        else if (sf == 1) { lregen = (b0 >> 4) | ((uint32_t)src[1] << 4); lhdr = 2; }
+        else { lregen = (b0 >> 4) | ((uint32_t)src[1] << 4) | ((uint32_t)src[2] << 12); lhdr = 3; }
+        lcomp = ltype == 0 ? lregen : 1;
+    } else {
+        if (sf < 2) { const uint32_t v = src[0] | (src[1] << 8) | ((uint32_t)src[2] << 16); lregen = (v >> 4) & 0x3FF; lcomp = (v >> 14) & 0x3FF; lhdr = 3; streams = sf == 0 ? 1 : 4; }
+        else if (sf == 2) { const uint32_t v = ldg_le32(src); lregen = (v >> 4) & 0x3FFF; lcomp = (v >> 18) & 0x3FFF; lhdr = 4; streams = 4; }
+        else { const uint64_t v = (uint64_t)ldg_le32(src) | ((uint64_t)src[4] << 32); lregen = (uint32_t)((v >> 4) & 0x3FFFF); lcomp = (uint32_t)((v >> 22) & 0x3FFFF); lhdr = 5; streams = 4; }
+    }
+    if (lhdr + lcomp > n || lregen != B.regen_hint) return ZMT_ST_BLOCK;
+    const uint8_t* lp = src + lhdr;
+    if (lit_done) { }                                              // literals already decoded by zstd_literals_kernel
+    else if (ltype == 0) { for (uint32_t i = lane; i < lregen; i += 32) lit[i] = lp[i]; }
+    else if (ltype == 1) { const uint8_t v = lp[0]; for (uint32_t i = lane; i < lregen; i += 32) lit[i] = v; }
+    else {
+        uint32_t tbytes = 0;
+        if (ltype == 2) {
+            { const uint32_t hr = zd_huf_build(W, lp, lcomp, lane, &tbytes); if (hr) return hr; }
         } else {
-            // treeless: reuse the previous block's table (frame-sequential pass only)
+            // treeless: reuse the previous block's table (frame-sequential pass, or rebuilt from the source block's description)
             if (!fs) return ZD_NEEDS_SEQ;
             if (W.hufbits == 0) return ZMT_ST_BLOCK;
         }
@@ -320,6 +372,7 @@ __device__ uint32_t zd_block(ZWarpTabs& W, const uint8_t* __restrict__ src, uint
     const uint8_t* qp = src + lhdr + lcomp;
     uint32_t qn = n - lhdr - lcomp;
     uint32_t rc = 0, total_ml = 0;
+    if (seq_done) { *regen_out = lregen + seq_ml; return 0; }      // sequences already decoded by zstd_seq_predef_kernel
     if (lane == 0) {
         do {
             if (qn < 1) { rc = ZMT_ST_BLOCK; break; }
@@ -355,7 +408,8 @@ __device__ uint32_t zd_block(ZWarpTabs& W, const uint8_t* __restrict__ src, uint
                 const uint32_t ml = d_ml_base[mlc] + R.read(d_ml_bits[mlc]);
                 const uint32_t ll = d_ll_base[llc] + R.read(d_ll_bits[llc]);
                 uint32_t off;
-                if (ofv > 3) { off = ofv - 3; r2 = r1; r1 = r0; r0 = off; }
+                if (fs && fs->raw_offsets) off = ofv;             // block-parallel pass: zstd_resolve_offsets_kernel applies the repeat-offset rule
+                else if (ofv > 3) { off = ofv - 3; r2 = r1; r1 = r0; r0 = off; }
                 else {
                     if (!fs) { rc = ZD_NEEDS_SEQ; break; }        // repeat offsets need the frame's history
                     const uint32_t idx = ofv + (ll == 0 ? 1u : 0u);
@@ -373,7 +427,7 @@ __device__ uint32_t zd_block(ZWarpTabs& W, const uint8_t* __restrict__ src, uint
                     sOF = (eo & 0xFFFF) + R.read((eo >> 16) & 0xFF);
                 }
                 if (R.off < 0) { rc = ZMT_ST_BLOCK; break; }
-                ZDSeq q; q.ll = ll; q.off = off; q.ml = ml; q.pad = 0;
+                ZDSeq q; q.ll = ll; q.off = off; q.ml = ml; q.pad = (fs && fs->raw_offsets) ? 1u : 0u;
                 seqs[i] = q;
                 total_ml += ml;
             }
@@ -398,11 +452,272 @@ __device__ __forceinline__ void zd_load_predef(ZWarpTabs& W, uint32_t lane)
     __syncwarp();
 }
 
+// ---------------------------------------------------------------- kernel 0: sequences of predefined-table blocks, one LANE per block
+// The three interleaved FSE states of a block are one serial chain; a warp that walks one chain on one lane wastes 31
+// issue slots of every instruction (round 1: 1.56 active lanes per instruction, the kernel issue-bound at 71 %).  Blocks
+// whose three tables are the predefined ones (every block our encoder writes; `Compression_Modes` = 0) need no per-block
+// table memory, so here every lane walks the chain of its own block: 32 chains per warp instruction.  Blocks with
+// described / RLE / repeated tables are left to the warp-per-block kernel below (seq_done stays 0).
+#define ZS_THREADS 128
+__global__ void __launch_bounds__(ZS_THREADS)
+zstd_seq_predef_kernel(const uint8_t* __restrict__ in, const ZBlk* __restrict__ blocks, uint32_t nblocks, const uint32_t* __restrict__ frame_seq,
+                       uint8_t* __restrict__ scratch, uint32_t* __restrict__ seq_done, uint32_t* __restrict__ seq_ml, uint32_t* __restrict__ status)
+{
+    __shared__ uint32_t pll[64], pof[32], pml[64], llx[36], mlx[53];      // FSE entries; base | bits << 24
+    for (uint32_t i = threadIdx.x; i < 64; i += ZS_THREADS) {
+        pll[i] = ((uint32_t)d_fse_ll.sym[i] << 24) | ((uint32_t)d_fse_ll.nb[i] << 16) | d_fse_ll.base[i];
+        pml[i] = ((uint32_t)d_fse_ml.sym[i] << 24) | ((uint32_t)d_fse_ml.nb[i] << 16) | d_fse_ml.base[i];
+        if (i < 32) pof[i] = ((uint32_t)d_fse_of.sym[i] << 24) | ((uint32_t)d_fse_of.nb[i] << 16) | d_fse_of.base[i];
+        if (i < 36) llx[i] = d_ll_base[i] | ((uint32_t)d_ll_bits[i] << 24);
+        if (i < 53) mlx[i] = d_ml_base[i] | ((uint32_t)d_ml_bits[i] << 24);
+    }
+    __syncthreads();
+    const uint32_t b = blockIdx.x * ZS_THREADS + threadIdx.x;
+    if (b >= nblocks) return;
+    const ZBlk B = blocks[b];
+    if (B.type != ZB_CMP || (frame_seq[B.frame] & ZF_NEEDS_SEQ)) return;
+    const uint8_t* src = in + B.comp_off;
+    const uint32_t n = B.comp_size;
+    // literals section header -> start of the sequences section (validated again by the literal decoder)
+    if (n < 1) return;
+    const uint32_t b0 = src[0], ltype = b0 & 3, sf = (b0 >> 2) & 3;
+    uint32_t lcomp, lhdr;
+    if (ltype < 2) {
+        uint32_t lregen;
+        if (sf == 0 || sf == 2) { lregen = b0 >> 3; lhdr = 1; }
+        else if (sf == 1) { if (n < 2) return; lregen = (b0 >> 4) | ((uint32_t)src[1] << 4); lhdr = 2; }
+        else { if (n < 3) return; lregen = (b0 >> 4) | ((uint32_t)src[1] << 4) | ((uint32_t)src[2] << 12); lhdr = 3; }
+        lcomp = ltype == 0 ? lregen : 1;
+    } else {
+        if (n < 5) return;
+        if (sf < 2) { const uint32_t v = src[0] | (src[1] << 8) | ((uint32_t)src[2] << 16); lcomp = (v >> 14) & 0x3FF; lhdr = 3; }
+        else if (sf == 2) { const uint32_t v = ldg_le32(src); lcomp = (v >> 18) & 0x3FFF; lhdr = 4; }
+        else { const uint64_t v = (uint64_t)ldg_le32(src) | ((uint64_t)src[4] << 32); lcomp = (uint32_t)((v >> 22) & 0x3FFFF); lhdr = 5; }
+    }
+    if ((uint64_t)lhdr + lcomp + 1 > n) return;
+    const uint8_t* qp = src + lhdr + lcomp;
+    uint32_t qn = n - lhdr - lcomp;
+    uint32_t nseq; const uint32_t q0 = qp[0];
+    uint32_t used = 1;
+    if (q0 == 0) nseq = 0;
+    else if (q0 < 128) nseq = q0;
+    else if (q0 < 255) { if (qn < 2) return; nseq = ((q0 - 128) << 8) + qp[1]; used = 2; }
+    else { if (qn < 3) return; nseq = qp[1] + (qp[2] << 8) + 0x7F00; used = 3; }
+    if (nseq != B.nseq) return;                               // the general path reports it
+    if (nseq == 0) { if (used == qn) { seq_ml[b] = 0; seq_done[b] = 1; } return; }
+    if (qn < used + 1 || qp[used] != 0) return;               // not all-predefined: general path
+    qp += used + 1; qn -= used + 1;
+    BackBits R;
+    if (!R.init(qp, qn)) return;
+    ZDSeq* seqs = reinterpret_cast<ZDSeq*>(scratch + B.seq_off);
+    uint32_t sLL = R.read(6), sOF = R.read(5), sML = R.read(6);
+    uint32_t total_ml = 0;
+    for (uint32_t i = 0; i < nseq; i++) {
+        const uint32_t eo = pof[sOF], em = pml[sML], el = pll[sLL];
+        const uint32_t ofc = eo >> 24, mlc = em >> 24, llc = el >> 24;
+        uint32_t ofv = 1u << ofc;
+        if (ofc > 24) { ofv += R.read(ofc - 16) << 16; ofv += R.read(16); } else ofv += R.read(ofc);
+        const uint32_t mx = mlx[mlc], lx = llx[llc];
+        const uint32_t ml = (mx & 0xFFFFFF) + R.read(mx >> 24);
+        const uint32_t ll = (lx & 0xFFFFFF) + R.read(lx >> 24);
+        if (ofv <= 3) {                                        // repeat offset: needs the frame's history -> frame-sequential pass
+            atomicMax(&status[B.frame], ZD_NEEDS_SEQ | 0x8000u);
+            return;
+        }
+        if (i + 1 < nseq) {
+            sLL = (el & 0xFFFF) + R.read((el >> 16) & 0xFF);
+            sML = (em & 0xFFFF) + R.read((em >> 16) & 0xFF);
+            sOF = (eo & 0xFFFF) + R.read((eo >> 16) & 0xFF);
+        }
+        if (R.off < 0) return;                                 // malformed: the general path redoes the block and reports it
+        ZDSeq q; q.ll = ll; q.off = ofv - 3; q.ml = ml; q.pad = 0;
+        seqs[i] = q;
+        total_ml += ml;
+    }
+    if (R.off != 0) return;
+    seq_ml[b] = total_ml; seq_done[b] = 1;
+}
+
+// ---------------------------------------------------------------- kernel 0b: Huffman literals, 8 blocks per warp
+// A block's literals are 4 independent Huffman streams: one warp per block keeps 4 lanes busy.  Here a warp takes 8
+// blocks: lane 4g + j decodes stream j of block g, every group of 4 lanes builds its block's decoding table in its own
+// 4 KiB of shared memory (weights direct or FSE-coded, counting sort by weight, fill).  Handles 4-stream
+// Huffman-compressed literals with their own tree (what our encoder and libzstd emit for all but tiny blocks); raw / RLE /
+// single-stream / treeless literals stay with the warp-per-block kernel (lit_done stays 0), and so does any block this
+// kernel finds malformed, so that errors are reported in one place.  Treeless literals take the tree from the block
+// the host scan named (ZBlk::huf_src).
+#define ZL_WARPS 2
+#define ZL_GROUPS 8
+struct ZLitGroup {
+    uint16_t huf[2048];            // (nbBits << 8) | symbol
+    uint8_t  wts[256];
+    uint16_t start[256];           // first table index of every symbol
+    uint32_t wtab[64];             // FSE table of the weights
+    int16_t  norm[64];
+    uint32_t next[16];             // counting sort cursors per weight
+};
+
+__global__ void __launch_bounds__(32 * ZL_WARPS)
+zstd_literals_kernel(const uint8_t* __restrict__ in, const ZBlk* __restrict__ blocks, uint32_t nblocks, const uint32_t* __restrict__ frame_seq,
+                     uint8_t* __restrict__ scratch, uint32_t* __restrict__ lit_done)
+{
+    extern __shared__ __align__(16) uint8_t zl_smem[];
+    ZLitGroup* G = reinterpret_cast<ZLitGroup*>(zl_smem) + ((threadIdx.x >> 5) * ZL_GROUPS + ((threadIdx.x & 31) >> 2));
+    const uint32_t lane = threadIdx.x & 31, j = lane & 3;
+    const uint32_t gmask = 0xFu << (lane & ~3u);                       // the 4 lanes of this group
+    const uint32_t b = (blockIdx.x * ZL_WARPS + (threadIdx.x >> 5)) * ZL_GROUPS + (lane >> 2);
+    bool ok = b < nblocks;
+    ZBlk B; B.type = ZB_RAW; B.comp_size = 0; B.comp_off = 0; B.frame = 0; B.regen_hint = 0; B.lit_off = 0; B.huf_src = ZB_SELF;
+    if (ok) { B = blocks[b]; ok = B.type == ZB_CMP && B.comp_size >= 3; }
+    const uint8_t* src = in + B.comp_off;
+    const uint32_t n = B.comp_size;
+    uint32_t lregen = 0, lcomp = 0, lhdr = 0, ltype = 0, sf = 0;
+    if (ok) {
+        ok = zd_lit_header(src, n, &lhdr, &lcomp, &lregen, &ltype, &sf) && ltype >= 2 && lregen == B.regen_hint && lcomp >= 1;
+        if (ok && ltype == 3 && (!(frame_seq[B.frame] & ZF_NEEDS_SEQ) || B.huf_src >= nblocks)) ok = false;     // treeless needs the host-named source block
+    }
+    const uint32_t nstreams = sf == 0 ? 1u : 4u;
+    // the tree description: in this block's own literals section, or (treeless) in the block that last described one
+    const uint8_t* lp = src + lhdr;                                     // own literals section content
+    const uint8_t* dlp = lp; uint32_t dcomp = lcomp;
+    if (ok && ltype == 3) {
+        const ZBlk S = blocks[B.huf_src];
+        uint32_t sh, sc, sr, st, ssf;
+        if (S.type != ZB_CMP || !zd_lit_header(in + S.comp_off, S.comp_size, &sh, &sc, &sr, &st, &ssf) || st != 2 || sc < 1) ok = false;
+        else { dlp = in + S.comp_off + sh; dcomp = sc; }
+    }
+    // ---- weights
+    uint32_t nw = 0, tbytes = 0;
+    if (ok) {
+        const uint32_t hb = dlp[0];
+        if (hb >= 128) {
+            nw = hb - 127; tbytes = 1 + (nw + 1) / 2;
+            if (tbytes > dcomp) ok = false;
+            else for (uint32_t i = j; i < 256; i += 4) {
+                uint32_t w = 0;
+                if (i < nw) { const uint32_t by = dlp[1 + i / 2]; w = (i & 1) ? (by & 15) : (by >> 4); }
+                G->wts[i] = (uint8_t)w;
+            }
+        } else {
+            if (hb == 0 || 1 + hb > dcomp) ok = false;
+            else {
+                tbytes = 1 + hb;
+                uint32_t cnt = 0;
+                if (j == 0) {                                           // serial: at most 255 weights
+                    int nsym = 0, log = 0; bool good = true;
+                    const int hl = zd_read_ncount(dlp + 1, hb, G->norm, &nsym, &log, 6, 15);
+                    BackBits R;
+                    if (hl < 0 || !zd_fse_build(G->wtab, G->norm, nsym, log) || !R.init(dlp + 1 + hl, hb - (uint32_t)hl)) good = false;
+                    if (good) {
+                        uint32_t s1 = R.read((uint32_t)log), s2 = R.read((uint32_t)log);
+                        if (R.off < 0) good = false;
+                        while (good) {
+                            if (cnt >= 254) { good = false; break; }
+                            uint32_t e = G->wtab[s1]; G->wts[cnt++] = (uint8_t)(e >> 24); s1 = (e & 0xFFFF) + R.read((e >> 16) & 0xFF);
+                            if (R.off < 0) { G->wts[cnt++] = (uint8_t)(G->wtab[s2] >> 24); break; }
+                            if (cnt >= 254) { good = false; break; }
+                            e = G->wtab[s2]; G->wts[cnt++] = (uint8_t)(e >> 24); s2 = (e & 0xFFFF) + R.read((e >> 16) & 0xFF);
+                            if (R.off < 0) { G->wts[cnt++] = (uint8_t)(G->wtab[s1] >> 24); break; }
+                        }
+                    }
+                    if (!good) cnt = 0xFFFFFFFFu;
+                }
+                cnt = __shfl_sync(gmask, cnt, lane & ~3u);
+                if (cnt == 0xFFFFFFFFu) ok = false; else nw = cnt;
+            }
+        }
+    }
+    __syncwarp();
+    if (ok && dlp[0] < 128) for (uint32_t i = nw + j; i < 256; i += 4) G->wts[i] = 0;
+    __syncwarp();
+    // ---- table: total weight -> maxbits and the implied last weight; counting sort by weight; fill
+    uint32_t maxbits = 0;
+    {
+        uint32_t total = 0;
+        if (ok) for (uint32_t i = j; i < nw; i += 4) { const uint32_t w = G->wts[i]; if (w > 11) total += 1u << 20; else if (w) total += 1u << (w - 1); }
+        total += __shfl_xor_sync(ZMT_FULL_MASK, total, 1);
+        total += __shfl_xor_sync(ZMT_FULL_MASK, total, 2);
+        if (ok) {
+            if (total == 0 || total >= 2048) ok = false;
+            else {
+                maxbits = 32 - __clz(total);
+                const uint32_t left = (1u << maxbits) - total;
+                if (left == 0 || (left & (left - 1)) || maxbits > 11) ok = false;
+                else if (j == 0) G->wts[nw] = (uint8_t)(32 - __clz(left));
+            }
+        }
+    }
+    __syncwarp();
+    if (ok && j == 0) {
+        uint32_t cntw[12];
+#pragma unroll
+        for (int w = 0; w < 12; w++) cntw[w] = 0;
+        for (uint32_t s2 = 0; s2 <= nw; s2++) {
+            const uint32_t w = G->wts[s2];
+#pragma unroll
+            for (int k = 1; k < 12; k++) cntw[k] += (w == (uint32_t)k) ? 1u : 0u;
+        }
+        uint32_t acc = 0;
+#pragma unroll
+        for (int k = 1; k < 12; k++) { G->next[k] = acc; acc += cntw[k] << (k - 1); }
+        for (uint32_t s2 = 0; s2 <= nw; s2++) {
+            const uint32_t w = G->wts[s2];
+            if (w && w < 12) { const uint32_t p0 = G->next[w]; G->start[s2] = (uint16_t)p0; G->next[w] = p0 + (1u << (w - 1)); }
+        }
+    }
+    __syncwarp();
+    if (ok) for (uint32_t s2 = j; s2 <= nw; s2 += 4) {
+        const uint32_t w = G->wts[s2];
+        if (!w || w > 11) continue;
+        const uint16_t e = (uint16_t)(((maxbits + 1 - w) << 8) | s2);
+        const uint32_t p0 = G->start[s2], cnt = 1u << (w - 1);
+        for (uint32_t k = 0; k < cnt; k++) G->huf[p0 + k] = e;
+    }
+    __syncwarp();
+    // ---- the streams (4 with a 6-byte jump table, or 1)
+    const uint32_t tb_own = ltype == 2 ? tbytes : 0u;                    // description bytes inside this block's own section
+    if (ok && tb_own + (nstreams == 4 ? 6u : 0u) > lcomp) ok = false;
+    bool fine = true;
+    if (ok && j < nstreams) {
+        const uint8_t* sp = lp + tb_own;
+        uint32_t ssz, spos, cnt, per = lregen;
+        if (nstreams == 4) {
+            const uint32_t s1 = sp[0] | (sp[1] << 8), s2 = sp[2] | (sp[3] << 8), s3 = sp[4] | (sp[5] << 8);
+            const uint32_t body = lcomp - tb_own - 6;
+            per = (lregen + 3) / 4;
+            if (s1 + s2 + s3 > body || per * 3 > lregen) fine = false;
+            ssz = j == 0 ? s1 : j == 1 ? s2 : j == 2 ? s3 : body - s1 - s2 - s3;
+            spos = j == 0 ? 0 : j == 1 ? s1 : j == 2 ? s1 + s2 : s1 + s2 + s3;
+            cnt = j < 3 ? per : lregen - 3 * per;
+            sp += 6;
+        } else { ssz = lcomp - tb_own; spos = 0; cnt = lregen; }
+        if (fine) {
+            uint8_t* o = scratch + B.lit_off + j * per;
+            BackBits R;
+            if (!R.init(sp + spos, ssz)) fine = false;
+            else {
+                const uint32_t msk = (1u << maxbits) - 1;
+                uint32_t st = R.read(maxbits);
+                for (uint32_t i = 0; i < cnt; i++) {
+                    const uint32_t e = G->huf[st], nb = e >> 8;
+                    o[i] = (uint8_t)e;
+                    st = ((st << nb) & msk) | R.read(nb);
+                }
+                if (R.off != -(int32_t)maxbits) fine = false;
+            }
+        }
+    }
+    // all 4 streams of the block must agree
+    const uint32_t good = __ballot_sync(ZMT_FULL_MASK, ok && fine);
+    if (ok && j == 0 && ((good >> (lane & ~3u)) & 0xFu) == 0xFu) lit_done[b] = 1;
+}
+
 // ---------------------------------------------------------------- kernel 1a: block-parallel entropy decode (self-contained blocks)
 #define ZD_WARPS 4
 __global__ void __launch_bounds__(32 * ZD_WARPS)
 zstd_entropy_kernel(const uint8_t* __restrict__ in, const ZBlk* __restrict__ blocks, uint32_t nblocks, const uint32_t* __restrict__ frame_seq,
-                    uint8_t* __restrict__ scratch, uint32_t* __restrict__ regen, uint32_t* __restrict__ status)
+                    uint8_t* __restrict__ scratch, uint32_t* __restrict__ regen, uint32_t* __restrict__ status,
+                    const uint32_t* __restrict__ seq_done, const uint32_t* __restrict__ seq_ml, const uint32_t* __restrict__ lit_done)
 {
     __shared__ ZWarpTabs tabs[ZD_WARPS];
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -411,14 +726,148 @@ zstd_entropy_kernel(const uint8_t* __restrict__ in, const ZBlk* __restrict__ blo
     const ZBlk B = blocks[b];
     if (B.type != ZB_CMP) { if (lane == 0) regen[b] = B.regen_hint; return; }
     if (frame_seq[B.frame] & ZF_NEEDS_SEQ) return;           // this frame goes through the frame-sequential pass
+    if (seq_done[b] && lit_done[b]) { if (lane == 0) regen[b] = B.regen_hint + seq_ml[b]; return; }    // nothing left for this block
     ZWarpTabs& W = tabs[wid];
     zd_load_predef(W, lane);
     uint32_t rg = 0;
-    const uint32_t rc = zd_block(W, in + B.comp_off, B.comp_size, B, scratch + B.lit_off, reinterpret_cast<ZDSeq*>(scratch + B.seq_off), nullptr, &rg, lane);
+    const uint32_t rc = zd_block(W, in + B.comp_off, B.comp_size, B, scratch + B.lit_off, reinterpret_cast<ZDSeq*>(scratch + B.seq_off), nullptr, &rg, lane,
+                                 seq_done[b], seq_ml[b], lit_done[b]);
     if (lane == 0) {
         if (rc == 0) regen[b] = rg;
         else if (rc == ZD_NEEDS_SEQ) atomicMax(&status[B.frame], ZD_NEEDS_SEQ | 0x8000u);      // flag (cleared by the sequential pass)
         else zd_fail(status, B.frame, rc);
+    }
+}
+
+// ---------------------------------------------------------------- kernel 1c: block-parallel entropy decode of frames with inter-block state
+// What libzstd emits for the reference: treeless literals, Repeat_Mode sequence tables and repeat
+// offsets tie the blocks of a frame together.  None of it needs the earlier blocks' DATA, only their section headers:
+// the host scan names, per block, the block whose header describes each table in use (ZBlk::*_src), this kernel rebuilds
+// those tables from there, decodes the block on its own warp like any other, and leaves the offsets as coded; the
+// repeat-offset rule is applied afterwards by one lane per frame (zstd_resolve_offsets_kernel).
+
+// Build sequence table `which` (0 LL, 1 OF, 2 ML) as block S describes it (mode 1 or 2 there).  One lane.
+__device__ bool zd_inherit_table(ZTabRef& cur, uint32_t which, const uint8_t* src, uint32_t n, ZWarpTabs& W)
+{
+    uint32_t lhdr, lcomp, lregen, lt, sf;
+    if (!zd_lit_header(src, n, &lhdr, &lcomp, &lregen, &lt, &sf)) return false;
+    const uint8_t* qp = src + lhdr + lcomp;
+    uint32_t qn = n - lhdr - lcomp;
+    if (qn < 1) return false;
+    const uint32_t q0 = qp[0];
+    const uint32_t used = q0 < 128 ? 1u : q0 < 255 ? 2u : 3u;
+    if (q0 == 0 || qn < used + 1) return false;
+    const uint32_t modes = qp[used];
+    qp += used + 1; qn -= used + 1;
+    uint32_t* const custom[3] = { W.ll, W.of, W.ml };
+    const uint32_t* const predef[3] = { W.pll, W.pof, W.pml };
+    const uint32_t plog[3] = { 6, 5, 6 };
+    const int maxlog[3] = { 9, 8, 9 }, maxsym[3] = { 35, 31, 52 };
+    for (uint32_t t = 0; t <= which; t++) {
+        const uint32_t mode = (modes >> (6 - 2 * t)) & 3;
+        if (t == which) {
+            if (mode != 1 && mode != 2) return false;              // the host scan only names blocks that describe the table
+            bool need = false;
+            return zd_seq_table(cur, mode, custom[t], predef[t], plog[t], W.norm, qp, qn, maxlog[t], maxsym[t], false, &need);
+        }
+        // skip the description of an earlier table
+        if (mode == 1) { if (qn < 1) return false; qp++; qn--; }
+        else if (mode == 2) {
+            int ns = 0, lg = 0;
+            const int u = zd_read_ncount(qp, qn, W.norm, &ns, &lg, maxlog[t], maxsym[t]);
+            if (u < 0) return false;
+            qp += u; qn -= (uint32_t)u;
+        }
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(32 * ZD_WARPS)
+zstd_entropy_dep_kernel(const uint8_t* __restrict__ in, const ZBlk* __restrict__ blocks, uint32_t nblocks, const uint32_t* __restrict__ frame_seq,
+                        uint8_t* __restrict__ scratch, uint32_t* __restrict__ regen, uint32_t* __restrict__ status, const uint32_t* __restrict__ lit_done)
+{
+    __shared__ ZWarpTabs tabs[ZD_WARPS];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t b = blockIdx.x * ZD_WARPS + wid;
+    if (b >= nblocks) return;
+    const ZBlk B = blocks[b];
+    if (B.type != ZB_CMP || !(frame_seq[B.frame] & ZF_NEEDS_SEQ)) return;
+    ZWarpTabs& W = tabs[wid];
+    zd_load_predef(W, lane);
+    ZFrameState fs; fs.rep[0] = 1; fs.rep[1] = 4; fs.rep[2] = 8; fs.have_tabs = true; fs.raw_offsets = true; fs.huf_ready = false;
+    fs.ll.t = W.pll; fs.ll.log = 6; fs.of.t = W.pof; fs.of.log = 5; fs.ml.t = W.pml; fs.ml.log = 6;
+    uint32_t bad = 0;
+    // ---- treeless literals: the tree of the block that last described one
+    if (!lit_done[b] && B.huf_src != ZB_SELF) {
+        if (B.huf_src >= nblocks) bad = 1;
+        else {
+            const ZBlk S = blocks[B.huf_src];
+            uint32_t lhdr, lcomp, lregen, lt, sf, tb;
+            if (S.type != ZB_CMP || !zd_lit_header(in + S.comp_off, S.comp_size, &lhdr, &lcomp, &lregen, &lt, &sf) || lt != 2 || lcomp < 1) bad = 1;
+            else if (zd_huf_build(W, in + S.comp_off + lhdr, lcomp, lane, &tb)) bad = 1;
+        }
+    }
+    // ---- repeated sequence tables: rebuilt from the describing block (lane 0), predefined ones are already in place
+    if (!bad && B.nseq) {
+        uint32_t r = 0;
+        if (lane == 0) {
+            const uint32_t srcs[3] = { B.ll_src, B.of_src, B.ml_src };
+            ZTabRef* const refs[3] = { &fs.ll, &fs.of, &fs.ml };
+            for (uint32_t t = 0; t < 3 && !r; t++) {
+                if (srcs[t] == ZB_SELF || srcs[t] == ZB_PREDEF) continue;
+                if (srcs[t] >= nblocks) { r = 1; break; }
+                const ZBlk S = blocks[srcs[t]];
+                if (S.type != ZB_CMP || !zd_inherit_table(*refs[t], t, in + S.comp_off, S.comp_size, W)) r = 1;
+            }
+        }
+        bad = __shfl_sync(ZMT_FULL_MASK, r, 0);
+        // the table references live in lane 0's registers: broadcast (pointers into this warp's shared tables)
+        fs.ll.t = (const uint32_t*)__shfl_sync(ZMT_FULL_MASK, (unsigned long long)fs.ll.t, 0); fs.ll.log = __shfl_sync(ZMT_FULL_MASK, fs.ll.log, 0);
+        fs.of.t = (const uint32_t*)__shfl_sync(ZMT_FULL_MASK, (unsigned long long)fs.of.t, 0); fs.of.log = __shfl_sync(ZMT_FULL_MASK, fs.of.log, 0);
+        fs.ml.t = (const uint32_t*)__shfl_sync(ZMT_FULL_MASK, (unsigned long long)fs.ml.t, 0); fs.ml.log = __shfl_sync(ZMT_FULL_MASK, fs.ml.log, 0);
+    }
+    __syncwarp();
+    if (bad) { if (lane == 0) zd_fail(status, B.frame, ZMT_ST_BLOCK); return; }
+    uint32_t rg = 0;
+    const uint32_t rc = zd_block(W, in + B.comp_off, B.comp_size, B, scratch + B.lit_off, reinterpret_cast<ZDSeq*>(scratch + B.seq_off), &fs, &rg, lane, 0, 0, lit_done[b]);
+    if (lane == 0) {
+        if (rc == 0) regen[b] = rg;
+        else zd_fail(status, B.frame, rc == ZD_NEEDS_SEQ ? ZMT_ST_BLOCK : rc);
+    }
+}
+
+// One LANE per frame: the repeat-offset rule (RFC 8878 3.1.1.5) over the frame's sequences in order.  Records written by
+// the block-parallel pass carry the coded offset value and pad = 1.
+__global__ void zstd_resolve_offsets_kernel(const ZBlk* __restrict__ blocks, const uint32_t* __restrict__ frame_first_blk, const uint32_t* __restrict__ frame_seq,
+                                            uint8_t* __restrict__ scratch, uint32_t* __restrict__ status, uint32_t nframes)
+{
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nframes || !(frame_seq[f] & ZF_NEEDS_SEQ) || (status[f] & 0xFF) != 0) return;
+    uint32_t r0 = 1, r1 = 4, r2 = 8;
+    for (uint32_t b = frame_first_blk[f]; b < frame_first_blk[f + 1]; b++) {
+        const ZBlk B = blocks[b];
+        if (B.type != ZB_CMP || B.nseq == 0) continue;
+        uint4* seqs = reinterpret_cast<uint4*>(scratch + B.seq_off);        // ZDSeq = {ll, off, ml, pad}
+        uint4 nx = seqs[0];
+        for (uint32_t i = 0; i < B.nseq; i++) {
+            const uint4 q = nx;
+            if (i + 1 < B.nseq) nx = seqs[i + 1];                          // next record in flight while this one resolves
+            if (q.w != 1) continue;                                         // not a raw record (block failed): leave it
+            const uint32_t ofv = q.y, ll = q.x;
+            uint32_t off;
+            if (ofv > 3) { off = ofv - 3; r2 = r1; r1 = r0; r0 = off; }
+            else {
+                const uint32_t idx = ofv + (ll == 0 ? 1u : 0u);
+                if (idx == 1) off = r0;
+                else {
+                    off = idx == 4 ? r0 - 1 : (idx == 2 ? r1 : r2);
+                    if (off == 0) { zd_fail(status, f, ZMT_ST_BLOCK); return; }
+                    if (idx > 2) r2 = r1;
+                    r1 = r0; r0 = off;
+                }
+            }
+            reinterpret_cast<uint32_t*>(seqs + i)[1] = off;
+        }
     }
 }
 
@@ -428,7 +877,7 @@ zstd_entropy_kernel(const uint8_t* __restrict__ in, const ZBlk* __restrict__ blo
 __global__ void __launch_bounds__(32 * ZD_WARPS)
 zstd_entropy_seq_kernel(const uint8_t* __restrict__ in, const ZBlk* __restrict__ blocks, const uint32_t* __restrict__ frame_first_blk,
                         const uint32_t* __restrict__ frame_seq, uint8_t* __restrict__ scratch, uint32_t* __restrict__ regen,
-                        uint32_t* __restrict__ status, uint32_t nframes)
+                        uint32_t* __restrict__ status, uint32_t nframes, uint32_t flagged_only)
 {
     __shared__ ZWarpTabs tabs[ZD_WARPS];
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -436,12 +885,14 @@ zstd_entropy_seq_kernel(const uint8_t* __restrict__ in, const ZBlk* __restrict__
     if (f >= nframes) return;
     const uint32_t st0 = status[f];
     const bool flagged = (st0 & 0x8000u) != 0;
-    if (!(frame_seq[f] & ZF_NEEDS_SEQ) && !flagged) return;
+    // flagged_only: frames the host scan marked were decoded block-parallel (kernel 1c); this pass then only takes the
+    // frames a block-parallel decoder flagged at run time (a repeat offset in a frame whose headers showed no state)
+    if (!flagged && (flagged_only || !(frame_seq[f] & ZF_NEEDS_SEQ))) return;
     __syncwarp();
     if (lane == 0 && flagged) status[f] = 0;
     ZWarpTabs& W = tabs[wid];
     zd_load_predef(W, lane);
-    ZFrameState fs; fs.rep[0] = 1; fs.rep[1] = 4; fs.rep[2] = 8; fs.have_tabs = false;
+    ZFrameState fs; fs.rep[0] = 1; fs.rep[1] = 4; fs.rep[2] = 8; fs.have_tabs = false; fs.raw_offsets = false; fs.huf_ready = false;
     fs.ll.t = fs.of.t = fs.ml.t = nullptr; fs.ll.log = fs.of.log = fs.ml.log = 0;
     for (uint32_t b = frame_first_blk[f]; b < frame_first_blk[f + 1]; b++) {
         const ZBlk B = blocks[b];
@@ -522,12 +973,13 @@ __device__ void zx_block(uint32_t b, uint32_t lane, const uint8_t* __restrict__ 
                 const uint32_t o = __shfl_sync(0xFFFFFFFFu, my_op, jl), l0 = __shfl_sync(0xFFFFFFFFu, my_lp, jl), n = __shfl_sync(0xFFFFFFFFu, ll, jl);
                 for (uint32_t k = lane; k < n; k += 32) dst[o + k] = lit[l0 + k];
             }
-            __syncwarp();
-            for (uint32_t jq = 0; jq < lim; jq++) {
-                const uint32_t qoff = __shfl_sync(0xFFFFFFFFu, off, jq), qml = __shfl_sync(0xFFFFFFFFu, ml, jq), mp = __shfl_sync(0xFFFFFFFFu, my_mp, jq);
-                if (qoff > mp) {
-                    // the match starts below this block: every earlier block it touches must be finished
-                    const uint64_t need = blk_abs + mp - qoff;                      // absolute output address of the first source byte
+            // ---- matches.  Any source below this block: wait (once per step) for the earlier blocks it touches.
+            {
+                unsigned long long need = ~0ull;                            // lowest absolute output address read by this step
+                if (lane < lim && ml && off > my_mp) need = blk_abs + my_mp - off;
+#pragma unroll
+                for (int x = 16; x > 0; x >>= 1) { const unsigned long long y = __shfl_xor_sync(0xFFFFFFFFu, need, x); need = y < need ? y : need; }
+                if (need != ~0ull) {
                     bool waited = false;
                     while (waited_to > 0 && blocks[waited_to - 1].frame == B.frame && blk_out[waited_to - 1] + regen[waited_to - 1] > need) {
                         waited_to--; waited = true;
@@ -536,6 +988,31 @@ __device__ void zx_block(uint32_t b, uint32_t lane, const uint8_t* __restrict__ 
                     __syncwarp();
                     if (waited) __threadfence();
                 }
+            }
+            __syncwarp();                                                   // this step's literals are in place
+            // A match whose source ends at or below the step's first output byte reads only finished data and cannot
+            // overlap its destination: those run lane-parallel (long ones by the whole warp); the others — reading
+            // output of this very step, or themselves — follow in sequence order.
+            const bool act = lane < lim && ml != 0;
+            const bool indep = act && (long long)my_mp - (long long)off + (long long)ml <= (long long)op;
+            if (indep && ml <= 32) {
+                uint8_t* d = dst + my_mp; const uint8_t* m = d - off;
+                uint32_t k = 0;
+                for (; k + 4 <= ml; k += 4) { const uint8_t a0 = m[k], a1 = m[k + 1], a2 = m[k + 2], a3 = m[k + 3]; d[k] = a0; d[k + 1] = a1; d[k + 2] = a2; d[k + 3] = a3; }
+                for (; k < ml; k++) d[k] = m[k];
+            }
+            uint32_t lm = __ballot_sync(0xFFFFFFFFu, indep && ml > 32);
+            while (lm) {
+                const int jl = __ffs(lm) - 1; lm &= lm - 1;
+                const uint32_t qoff = __shfl_sync(0xFFFFFFFFu, off, jl), qml = __shfl_sync(0xFFFFFFFFu, ml, jl), mp = __shfl_sync(0xFFFFFFFFu, my_mp, jl);
+                uint8_t* d = dst + mp; const uint8_t* m = d - qoff;
+                for (uint32_t k = lane; k < qml; k += 32) d[k] = m[k];
+            }
+            uint32_t dm = __ballot_sync(0xFFFFFFFFu, act && !indep);
+            if (dm) __syncwarp();
+            while (dm) {
+                const int jq = __ffs(dm) - 1; dm &= dm - 1;
+                const uint32_t qoff = __shfl_sync(0xFFFFFFFFu, off, jq), qml = __shfl_sync(0xFFFFFFFFu, ml, jq), mp = __shfl_sync(0xFFFFFFFFu, my_mp, jq);
                 uint8_t* d = dst + mp;
                 const uint8_t* m = d - qoff;
                 if (qoff >= qml) { for (uint32_t k = lane; k < qml; k += 32) d[k] = m[k]; }
@@ -543,6 +1020,7 @@ __device__ void zx_block(uint32_t b, uint32_t lane, const uint8_t* __restrict__ 
                 else { for (uint32_t k = lane; k < qml; k += 32) d[k] = m[k % qoff]; }
                 __syncwarp();
             }
+            __syncwarp();
             if (badmask) { bad = true; break; }
             op += __shfl_sync(0xFFFFFFFFu, it, cnt - 1);
             lp += __shfl_sync(0xFFFFFFFFu, il, cnt - 1);
@@ -732,6 +1210,7 @@ extern "C" int zmt_zstd_scan_frame_host2(const uint8_t* frame, size_t n, uint64_
     if (has_chk) *needs_seq |= ZF_CHECKSUM;
     if (no_size) *needs_seq |= ZF_NO_SIZE;
     bool first = true;
+    uint32_t last_huf = ZB_NONE, cur_src[3] = { ZB_NONE, ZB_NONE, ZB_NONE };     // block that last described the Huffman tree / each sequence table
     for (;;) {
         if (n - pos < 3) return ZMT_ST_TRUNCATED;
         const uint32_t bh = frame[pos] | (frame[pos + 1] << 8) | ((uint32_t)frame[pos + 2] << 16); pos += 3;
@@ -772,6 +1251,18 @@ extern "C" int zmt_zstd_scan_frame_host2(const uint8_t* frame, size_t n, uint64_
                 const uint32_t used = q0 == 0 ? 1u : q0 < 128 ? 1u : q0 < 255 ? 2u : 3u;
                 if (lt == 3) *needs_seq |= ZF_NEEDS_SEQ;
                 if (nseq && qn > used && q[used] != 0) *needs_seq |= ZF_NEEDS_SEQ;
+                const uint32_t me = *nblocks_io;
+                B.huf_src = ZB_SELF;
+                if (lt == 2) last_huf = me; else if (lt == 3) B.huf_src = last_huf;
+                B.ll_src = B.of_src = B.ml_src = ZB_SELF;
+                if (nseq && qn > used) {
+                    uint32_t* const dst3[3] = { &B.ll_src, &B.of_src, &B.ml_src };
+                    for (uint32_t t = 0; t < 3; t++) {
+                        const uint32_t mode = (q[used] >> (6 - 2 * t)) & 3;
+                        if (mode == 0) cur_src[t] = ZB_PREDEF; else if (mode != 3) cur_src[t] = me;
+                        *dst3[t] = (mode == 3) ? cur_src[t] : (mode == 0 ? ZB_PREDEF : ZB_SELF);
+                    }
+                }
             }
             B.comp_size = bs; B.regen_hint = lregen; B.nseq = nseq;
             B.seq_off = *scratch_used; *scratch_used += (((uint64_t)nseq * sizeof(ZDSeq)) + 15) & ~15ull;
@@ -794,7 +1285,7 @@ extern "C" size_t zmt_zstd_blk_desc_bytes(void) { return sizeof(ZBlk); }
 extern "C" size_t zmt_zstdd_workspace_bytes(uint32_t nframes, uint32_t nblocks, uint64_t scratch_bytes)
 {
     return (size_t)(((uint64_t)nblocks * 4 + 255) & ~255ull) * 2 + (((uint64_t)nblocks * 8 + 255) & ~255ull) + (((uint64_t)nframes * 8 + 255) & ~255ull)
-           + 256 + scratch_bytes + 1024;
+           + 256 + 3 * (size_t)(((uint64_t)nblocks * 4 + 255) & ~255ull) + scratch_bytes + 1024;
 }
 
 // d_blocks: nblocks descriptors (device copy of what zmt_zstd_scan_frame_host produced); d_frame_first_blk: nframes+1;
@@ -812,15 +1303,36 @@ extern "C" int zmt_zstd_decompress_device(const void* d_in, const void* d_blocks
     uint64_t* blk_out = (uint64_t*)w; w += (((uint64_t)nblocks * 8 + 255) & ~255ull);
     w += (((uint64_t)nframes * 8 + 255) & ~255ull);
     unsigned int* xticket = (unsigned int*)w; w += 256;
+    uint32_t* seq_done = (uint32_t*)w; w += (((uint64_t)nblocks * 4 + 255) & ~255ull);
+    uint32_t* seq_ml = (uint32_t*)w; w += (((uint64_t)nblocks * 4 + 255) & ~255ull);
+    uint32_t* lit_done = (uint32_t*)w; w += (((uint64_t)nblocks * 4 + 255) & ~255ull);
     uint8_t* scratch = w;
     cudaMemsetAsync(d_status, 0, (size_t)nframes * 4, stream);
     cudaMemsetAsync(regen, 0, (size_t)nblocks * 4, stream);
     cudaMemsetAsync(done, 0, (size_t)nblocks * 4, stream);
     zmt_prof_mark(ZMT_K_ZSTD_DECODE, stream, 0);
     if (nblocks) {
-        zstd_entropy_kernel<<<(nblocks + ZD_WARPS - 1) / ZD_WARPS, 32 * ZD_WARPS, 0, stream>>>((const uint8_t*)d_in, (const ZBlk*)d_blocks, nblocks, d_frame_seq, scratch, regen, d_status);
+        cudaMemsetAsync(seq_done, 0, (size_t)nblocks * 4, stream);
+        cudaMemsetAsync(lit_done, 0, (size_t)nblocks * 4, stream);
+        static const bool no_fast = getenv("ZSTDMT_B200_NO_FAST_ENTROPY") != nullptr;      // A/B knob: warp-per-block entropy decode only
+        if (!no_fast) {
+            const size_t lsm = sizeof(ZLitGroup) * ZL_GROUPS * ZL_WARPS;
+            cudaFuncSetAttribute(zstd_literals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm);
+            const uint32_t per = ZL_GROUPS * ZL_WARPS;
+            zstd_literals_kernel<<<(nblocks + per - 1) / per, 32 * ZL_WARPS, lsm, stream>>>((const uint8_t*)d_in, (const ZBlk*)d_blocks, nblocks, d_frame_seq, scratch, lit_done);
+        }
+        if (!no_fast)
+        zstd_seq_predef_kernel<<<(nblocks + ZS_THREADS - 1) / ZS_THREADS, ZS_THREADS, 0, stream>>>((const uint8_t*)d_in, (const ZBlk*)d_blocks, nblocks, d_frame_seq, scratch,
+                                                                                           seq_done, seq_ml, d_status);
+        zstd_entropy_kernel<<<(nblocks + ZD_WARPS - 1) / ZD_WARPS, 32 * ZD_WARPS, 0, stream>>>((const uint8_t*)d_in, (const ZBlk*)d_blocks, nblocks, d_frame_seq, scratch, regen, d_status,
+                                                                                           seq_done, seq_ml, lit_done);
+        if (!no_fast) {
+            zstd_entropy_dep_kernel<<<(nblocks + ZD_WARPS - 1) / ZD_WARPS, 32 * ZD_WARPS, 0, stream>>>((const uint8_t*)d_in, (const ZBlk*)d_blocks, nblocks, d_frame_seq, scratch, regen,
+                                                                                               d_status, lit_done);
+            zstd_resolve_offsets_kernel<<<(nframes + 63) / 64, 64, 0, stream>>>((const ZBlk*)d_blocks, d_frame_first_blk, d_frame_seq, scratch, d_status, nframes);
+        }
         zstd_entropy_seq_kernel<<<(nframes + ZD_WARPS - 1) / ZD_WARPS, 32 * ZD_WARPS, 0, stream>>>((const uint8_t*)d_in, (const ZBlk*)d_blocks, d_frame_first_blk, d_frame_seq,
-                                                                                           scratch, regen, d_status, nframes);
+                                                                                           scratch, regen, d_status, nframes, no_fast ? 0u : 1u);
     }
     zstd_offsets_kernel<<<(nframes + 127) / 128, 128, 0, stream>>>((const ZBlk*)d_blocks, nblocks, d_frame_first_blk, regen, blk_out, d_out_off, d_expect,
                                                                    (unsigned long long*)d_out_size, d_status, nframes);
