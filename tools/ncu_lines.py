@@ -18,14 +18,14 @@ for f in os.listdir(tmp):
         if m: cur = (os.path.basename(m.group(1)), int(m.group(2))); continue
         m = re.match(r"\s*/\*([0-9a-f]{4,})\*/", ln)
         if m and cur: line_of[int(m.group(1), 16)] = cur
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kname], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hi]
 iS, iI, iT = hdr.index("# Samples"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed")
 base = None; agg = collections.defaultdict(lambda: [0, 0, 0]); tot = 0
 for r in rows[hi + 1:]:
-    if len(r) <= iT: continue
+    if len(r) <= iT or r[0] == "Address" or not r[0].startswith("0x"): continue
     a = int(r[0], 16)
     if base is None: base = a
     k = line_of.get(a - base, ("?", 0))
@@ -36,6 +36,9 @@ for (f, l), v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:int(os.environ.g
     if f not in srcs:
         p = os.path.join(os.path.dirname(lib), "csrc", f)
         srcs[f] = open(p).read().splitlines() if os.path.exists(p) else []
+        if not srcs[f]:
+            p2 = os.path.join(os.path.dirname(os.path.dirname(lib)), "include", f)
+            srcs[f] = open(p2).read().splitlines() if os.path.exists(p2) else []
     text = srcs[f][l - 1].strip()[:100] if 0 < l <= len(srcs[f]) else ""
     print(f"{v[0]:8d} {v[0]/max(tot,1)*100:5.1f}%  inst={v[1]:11d} thr/inst={v[2]/max(v[1],1):5.1f}  {f}:{l:<4d} {text}")
 

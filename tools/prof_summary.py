@@ -3,7 +3,7 @@ import csv, os, subprocess, sys
 rep, kernel, name = sys.argv[1], sys.argv[2], sys.argv[3]
 note = sys.argv[4] if len(sys.argv) > 4 else ""
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--kernel-name", "regex:" + kernel], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, vals = rows[0], rows[1], rows[2]
 d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}

@@ -54,20 +54,12 @@ __device__ __forceinline__ void d_fail(uint32_t* status, uint32_t f, uint32_t co
     }
 }
 
+// whole-warp copy; long runs go through the 16-byte-store copier of common.cuh (re-aligns the source with funnel shifts;
+// may read up to 4 bytes past src + n: every source here is followed by at least an end mark or lies inside the output)
 __device__ __forceinline__ void warp_copy_lit(uint8_t* dst, const uint8_t* src, uint32_t n, uint32_t lane)
 {
-    if (n >= 64 && ((((uintptr_t)dst) ^ ((uintptr_t)src)) & 3) == 0) {
-        // same 4-byte phase: word copies in the middle
-        uint32_t head = (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3);
-        if (lane < head) dst[lane] = src[lane];
-        const uint32_t nw = (n - head) >> 2;
-        const uint32_t* s4 = reinterpret_cast<const uint32_t*>(src + head);
-        uint32_t* d4 = reinterpret_cast<uint32_t*>(dst + head);
-        for (uint32_t i = lane; i < nw; i += 32) d4[i] = s4[i];
-        for (uint32_t i = head + (nw << 2) + lane; i < n; i += 32) dst[i] = src[i];
-    } else {
-        for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
-    }
+    if (n >= 64) coop_copy_g2g(dst, src, n, lane, 32);
+    else for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
 }
 
 // ---------------------------------------------------------------- frame scan
@@ -222,25 +214,37 @@ __device__ uint32_t lzd_parse_block(uint8_t* win, uint8_t* J, const uint8_t* gsr
             reinterpret_cast<uint2*>(J)[lane] = make_uint2(j0, j1);
         }
         __syncwarp();
-        // ---- follow the chain: lane k keeps the start of the k-th sequence
-        uint32_t pr = 0, k = 0, myp = 0;
+        // ---- follow the chain: lane k keeps the start of the k-th sequence (relative to ip0).  Tokens with length
+        //      extensions (J = 0) are parsed right here by all lanes and handed to lane k, so nothing is parsed twice
+        uint32_t pr = 0, k = 0, myrel = 0;
         uint32_t fin = 0;                                   // 1: block ends with sequence k-1, 2: malformed
-        while (k < 32 && pr < LZD_NJ) {
-            if (lane == k) myp = ip0 + pr;
+        LzSeq s; s.lit = s.litpos = s.off = s.ml = 0; s.next = 0; s.st = 3;      // st 3: plain token, decoded below
+#pragma unroll 4
+        for (; k < 32; k++) {
+            if (pr >= LZD_NJ) break;
+            myrel = lane == k ? pr : myrel;
             uint32_t d = J[pr];
-            k++;
             if (d == 0) {
                 const LzSeq q = lzd_parse_seq(W, srcSize, ip0 + pr);
-                if (q.st) { fin = q.st; break; }
+                if (lane == k) s = q;
+                if (q.st) { fin = q.st; k++; break; }
                 d = q.next - (ip0 + pr);
             }
             pr += d;
         }
         if (fin == 2) return LZD_ERR;
         const uint32_t cnt = k;
-        // ---- every lane decodes its own sequence
-        LzSeq s; s.lit = s.litpos = s.off = s.ml = 0; s.st = 0;
-        if (lane < cnt) s = lzd_parse_seq(W, srcSize, myp);
+        // ---- plain tokens: literal length, match length and offset straight out of the window (the J rule keeps the
+        //      whole sequence inside it and in front of the block end)
+        if (lane < cnt && s.st == 3) {
+            const uint32_t r = myrel + sh;                                  // window index of the token
+            const uint32_t tok = win[r];
+            s.lit = tok >> 4; s.litpos = ip0 + myrel + 1;
+            const uint32_t o = r + 1 + s.lit;
+            s.off = win[o] | ((uint32_t)win[o + 1] << 8);
+            s.ml = (tok & 15) + 4; s.st = 0;
+        }
+        if (lane >= cnt) { s.lit = 0; s.ml = 0; s.st = 0; }
         bool bad = lane < cnt && (s.st == 2 || s.lit > dcap || s.ml > dcap);
         if (bad) { s.lit = 0; s.ml = 0; }
         const uint32_t tot = s.lit + s.ml;
@@ -254,8 +258,10 @@ __device__ uint32_t lzd_parse_block(uint8_t* win, uint8_t* J, const uint8_t* gsr
         if (s.lit && s.lit <= LZD_LONG) {
             uint8_t* d = dst + my_op;
             const uint32_t r = s.litpos - (uint32_t)W.pos;
-            if (r + s.lit <= LZD_WIN) { const uint8_t* sp = win + r; for (uint32_t i = 0; i < s.lit; i++) d[i] = sp[i]; }
-            else { const uint8_t* sp = gsrc + s.litpos; for (uint32_t i = 0; i < s.lit; i++) d[i] = sp[i]; }
+            const uint8_t* sp = (r + s.lit <= LZD_WIN) ? win + r : gsrc + s.litpos;      // generic pointer: shared or global
+            uint32_t i = 0;
+            for (; i + 4 <= s.lit; i += 4) { const uint8_t a = sp[i], b = sp[i + 1], c = sp[i + 2], e = sp[i + 3]; d[i] = a; d[i + 1] = b; d[i + 2] = c; d[i + 3] = e; }
+            for (; i < s.lit; i++) d[i] = sp[i];
         }
         uint32_t longmask = __ballot_sync(ZMT_FULL_MASK, s.lit > LZD_LONG);
         while (longmask) {
@@ -412,8 +418,20 @@ lz4_exec_blocks_kernel(uint8_t* __restrict__ out, const uint64_t* __restrict__ o
                         if (pv == LZD_DONE) prev_done = true;
                     }
                 }
-                const uint32_t d0 = __shfl_sync(ZMT_FULL_MASK, d, 0);
-                const bool indep = ml && sp + (int32_t)ml <= (int32_t)d0;   // source entirely below this step's first destination
+                // Which matches must wait for an earlier match of this very step?  Literals are already in place, so only
+                // the destinations [d_j, e_j) of matches j < k matter; they are sorted and disjoint.  a = first j whose
+                // destination ends above my source start (binary search over the lanes by shuffle); my source touches a
+                // destination of the step iff that j lies before me and starts below my source end.  A match that
+                // overlaps its own destination (offset < length) takes the ordered path too.
+                const int32_t e_end = ml ? (int32_t)(d + ml) : 0x7FFFFFFF, d_beg = ml ? (int32_t)d : 0x7FFFFFFF;
+                uint32_t a = 0;
+#pragma unroll
+                for (uint32_t stp = 16; stp > 0; stp >>= 1) {
+                    const int32_t v = __shfl_sync(ZMT_FULL_MASK, e_end, (a + stp - 1) & 31);
+                    if (v <= sp) a += stp;                                  // e_j <= sp: destination j lies entirely below my source
+                }
+                const int32_t da = __shfl_sync(ZMT_FULL_MASK, d_beg, a & 31);
+                const bool indep = ml && off >= ml && !(a < lane && da < sp + (int32_t)ml);
                 if (indep && ml <= LZD_LONG) {
                     uint8_t* dp = dst + d; const uint8_t* mp = dst + sp;
                     uint32_t i = 0;
