@@ -56,3 +56,21 @@ def test_round_robin_reassembly_world2(tmp_path):
     assert int(tot[0]) == NCHUNKS * CHUNK and int(tot[1]) == expect.size
     rc, back = o.orc_decode(o.CODEC_LZ4, merged, whole.size)
     assert rc == 0 and np.array_equal(back, whole)
+
+
+def test_dealt_streams_partition_the_global_stream_in_batches():
+    """bench.py deals chunks in batches of 8 (the product's slot granularity): rank r's share is
+    zmt_gen_stream_dealt(rank, world, batch); the shares must tile the one global stream, and every rank must see every
+    data class of the mix (the round-1 bench aliased class = chunk index mod 8 with rank = chunk index mod N)."""
+    import zstdmt_b200 as z
+    chunk, batch = 1 << 16, 8
+    for world in (1, 2, 4, 8):
+        per = 4 * batch                                             # chunks per rank
+        glob = z.gen_stream(z.GEN_MIX, per * world * chunk, chunk)
+        for r in range(world):
+            mine = z.gen_stream(z.GEN_MIX, per * chunk, chunk, deal=(r, world, batch))
+            for i in range(per):
+                g = (i // batch) * batch * world + r * batch + i % batch
+                assert np.array_equal(mine[i * chunk:(i + 1) * chunk], glob[g * chunk:(g + 1) * chunk]), (world, r, i)
+            classes = {((i // batch) * batch * world + r * batch + i % batch) & 7 for i in range(per)}
+            assert classes == set(range(8))

@@ -729,7 +729,9 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
         }
         c->insize += 16;
         if (is_skip(first) && is_zstd(first + 12)) { hdr_pending = true; first_payload_have = 4; }          // pzstd style
-        else if (is_zstd(first) && is_skip(first + 9)) {                                                       // zstdmt style: 9-byte empty frame + 12-byte header
+        else if (is_zstd(first) && rd32(first + 9) == MT_MAGIC_SKIPPABLE) {                                    // zstdmt style: 9-byte empty frame + 12-byte header
+            // (only the magic can be tested here, as IsZstd_Skippable does, zstd-mt_decompress.c:156-159: 7 of the header's 12
+            //  bytes are in hand; the size field is checked with the assembled header.  Round 1 read its 4 bytes past the buffer.)
             uint8_t tmp[12]; memcpy(tmp, first + 9, 7);
             size_t e2 = read_some(E, rw, tmp + 7, 5, &got); if (e2) return e2;
             if (got != 5) return E.data_error;

@@ -149,6 +149,27 @@ __device__ __forceinline__ uint32_t lzw_byte(const LzWin& W, uint32_t q)
     return r < LZD_WIN ? W.w[r] : W.g[q];
 }
 
+// Sequence parser for the common extended tokens, all reads out of the staged window without per-byte range tests: taken
+// when the whole sequence header (token, up to 2 + 2 extension bytes, offset) provably lies inside the window and in front
+// of the block end; anything else goes through lzd_parse_seq.  Returns false if it does not apply.
+__device__ __forceinline__ bool lzd_parse_seq_win(const LzWin& W, uint32_t srcSize, uint32_t p, LzSeq& s)
+{
+    const uint32_t r = p - (uint32_t)W.pos;
+    if (r + 24 > LZD_WIN || p + 24 > srcSize) return false;            // room for token + 2 ext + (lit handled below) + offset + 2 ext
+    const uint8_t* w = W.w + r;
+    const uint32_t tok = w[0];
+    uint32_t lit = tok >> 4, q = 1;
+    if (lit == 15) { const uint32_t b = w[1]; lit += b; q = 2; if (b == 255) { const uint32_t c = w[2]; if (c == 255) return false; lit += c; q = 3; } }
+    if (r + q + lit + 6 > LZD_WIN || p + q + lit + 6 > srcSize) return false;
+    s.lit = lit; s.litpos = p + q;
+    const uint8_t* o = w + q + lit;
+    s.off = o[0] | ((uint32_t)o[1] << 8);
+    uint32_t ml = tok & 15, e = 2;
+    if (ml == 15) { const uint32_t b = o[2]; ml += b; e = 3; if (b == 255) { const uint32_t c = o[3]; if (c == 255) return false; ml += c; e = 4; } }
+    s.ml = ml + 4; s.next = p + q + lit + e; s.st = 0;
+    return true;
+}
+
 // general sequence parser (any literal / match length, end of block); every read is bounds-checked against srcSize
 __device__ __forceinline__ LzSeq lzd_parse_seq(const LzWin& W, uint32_t srcSize, uint32_t p)
 {
@@ -198,7 +219,9 @@ __device__ uint32_t lzd_parse_block(uint8_t* win, uint8_t* J, const uint8_t* gsr
             reinterpret_cast<uint4*>(win)[lane] = v;
         }
         __syncwarp();
-        // ---- J[pr] = distance to the next token if a plain token (no length extension, not near the end) starts at ip0 + pr, else 0
+        // ---- J[pr] = distance to the next token if a short-literal token starts at ip0 + pr (literal length < 15; match
+        //      length plain or extended by ONE byte < 255 — matches of 19..273 bytes are the bulk of the extended tokens on
+        //      structured data), and the next token lies in front of the block end; else 0 (the chain follow parses it)
         {
             const uint32_t base = sh + 8 * lane;
             const uint32_t w0 = lds32u(win, base), w1 = lds32u(win, base + 4);
@@ -206,8 +229,11 @@ __device__ uint32_t lzd_parse_block(uint8_t* win, uint8_t* J, const uint8_t* gsr
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const uint32_t tok = ((j < 4 ? w0 : w1) >> (8 * (j & 3))) & 0xFF;
-                const uint32_t lit = tok >> 4, d = 3 + lit;
-                const bool fast = lit != 15 && (tok & 15) != 15 && ip0 + 8 * lane + j + d < srcSize;
+                const uint32_t lit = tok >> 4;
+                uint32_t d = 3 + lit;
+                bool fast = lit != 15;
+                if ((tok & 15) == 15) { fast = fast && win[base + j + d] != 255; d++; }      // lit < 15: index <= 15 + 255 + 18 < LZD_WIN
+                fast = fast && ip0 + 8 * lane + j + d < srcSize;
                 const uint32_t v = fast ? d : 0;
                 if (j < 4) j0 |= v << (8 * j); else j1 |= v << (8 * (j - 4));
             }
@@ -225,7 +251,8 @@ __device__ uint32_t lzd_parse_block(uint8_t* win, uint8_t* J, const uint8_t* gsr
             myrel = lane == k ? pr : myrel;
             uint32_t d = J[pr];
             if (d == 0) {
-                const LzSeq q = lzd_parse_seq(W, srcSize, ip0 + pr);
+                LzSeq q;
+                if (!lzd_parse_seq_win(W, srcSize, ip0 + pr, q)) q = lzd_parse_seq(W, srcSize, ip0 + pr);
                 if (lane == k) s = q;
                 if (q.st) { fin = q.st; k++; break; }
                 d = q.next - (ip0 + pr);
@@ -243,6 +270,7 @@ __device__ uint32_t lzd_parse_block(uint8_t* win, uint8_t* J, const uint8_t* gsr
             const uint32_t o = r + 1 + s.lit;
             s.off = win[o] | ((uint32_t)win[o + 1] << 8);
             s.ml = (tok & 15) + 4; s.st = 0;
+            if ((tok & 15) == 15) s.ml += win[o + 2];                        // the one extension byte the J rule admitted
         }
         if (lane >= cnt) { s.lit = 0; s.ml = 0; s.st = 0; }
         bool bad = lane < cnt && (s.st == 2 || s.lit > dcap || s.ml > dcap);
@@ -333,6 +361,7 @@ lz4_parse_blocks_kernel(const uint8_t* __restrict__ in, const uint8_t* __restric
 // A window whose frames have very different block counts would mostly hand out empty tickets; it falls back to
 // frame-major order (flag in the top bit of its base).
 #define LZX_WIN 16384u
+#define LZX_SPAN 2048u        // bytes of output a step may span: staged in shared memory
 __global__ void __launch_bounds__(256)
 lz4_ticket_windows_kernel(const uint64_t* __restrict__ first_slot, uint32_t nframes, unsigned long long* __restrict__ wbase)
 {
@@ -362,6 +391,7 @@ lz4_exec_blocks_kernel(uint8_t* __restrict__ out, const uint64_t* __restrict__ o
                        uint32_t* __restrict__ prog, const uint32_t* __restrict__ status, const uint32_t* __restrict__ needs_seq,
                        unsigned long long* __restrict__ ticket, const unsigned long long* __restrict__ wbase, uint32_t nframes, uint32_t slot_cap)
 {
+    __shared__ __align__(16) uint8_t stage[LZD_WARPS][LZX_SPAN + 32];
     const uint32_t lane = threadIdx.x & 31;
     if (first_slot[nframes] > slot_cap) return;             // the scan reported the undersized table per frame
     const uint32_t nwin = (nframes + LZX_WIN - 1) / LZX_WIN;
@@ -399,10 +429,37 @@ lz4_exec_blocks_kernel(uint8_t* __restrict__ out, const uint64_t* __restrict__ o
             const bool publish = !(B.flags & LZB_LAST) && (tab[t + 1].flags & LZB_LINKED);     // the next block may read this one
             bool prev_done = !linked;
             uint32_t since_pub = 0;
-            for (uint32_t base = 0; base < B.nrec; base += 32) {
+            uint8_t* const S = stage[threadIdx.x >> 5];
+            for (uint32_t base = 0; base < B.nrec;) {
                 const uint32_t cnt = B.nrec - base < 32 ? B.nrec - base : 32;
                 uint32_t d = 0, ml = 0, off = 0;
                 if (lane < cnt) { const unsigned long long r = R[base + lane]; d = (uint32_t)r & 0xFFFFFFu; ml = (uint32_t)(r >> 24) & 0xFFFFFFu; off = (uint32_t)(r >> 48); }
+                const uint32_t d0 = __shfl_sync(ZMT_FULL_MASK, d, 0);
+                // ---- the step = the longest prefix of these records whose destinations fit the staging window [d0, d0 + LZX_SPAN)
+                const uint32_t nfit = __popc(__ballot_sync(ZMT_FULL_MASK, ml && d + ml - d0 <= LZX_SPAN));       // destinations are sorted: a prefix
+                if (nfit == 0) {
+                    // one match longer than the window: straight in global memory, by the whole warp
+                    const uint32_t qml = __shfl_sync(ZMT_FULL_MASK, ml, 0), qoff = __shfl_sync(ZMT_FULL_MASK, off, 0);
+                    if (!prev_done && qoff > d0) {
+                        const int64_t e = (int64_t)blkmax + (int64_t)d0 - qoff + qml;
+                        const uint32_t need = e > (int64_t)blkmax ? blkmax : (uint32_t)e;
+                        uint32_t pv = 0;
+                        if (lane == 0) { while ((pv = vprog[t - 1]) < need) __nanosleep(100); }
+                        pv = __shfl_sync(ZMT_FULL_MASK, pv, 0);
+                        __threadfence();
+                        if (pv == LZD_DONE) prev_done = true;
+                    }
+                    uint8_t* dp = dst + d0;
+                    const uint8_t* m = dp - qoff;
+                    if (qoff >= qml) warp_copy_lit(dp, m, qml, lane);
+                    else if (qoff >= 32) { for (uint32_t i = 0; i < qml; i += 32) { if (i + lane < qml) dp[i + lane] = m[i + lane]; __syncwarp(); } }
+                    else { for (uint32_t i = lane; i < qml; i += 32) dp[i] = m[i % qoff]; }
+                    __syncwarp();
+                    base += 1;
+                    continue;
+                }
+                if (lane >= nfit) ml = 0;
+                const uint32_t span = __shfl_sync(ZMT_FULL_MASK, d + ml, nfit - 1) - d0;
                 const int32_t sp = (int32_t)d - (int32_t)off;           // block-relative source; negative = previous block
                 if (!prev_done) {
                     // bytes of the previous block this step needs complete
@@ -418,11 +475,22 @@ lz4_exec_blocks_kernel(uint8_t* __restrict__ out, const uint64_t* __restrict__ o
                         if (pv == LZD_DONE) prev_done = true;
                     }
                 }
-                // Which matches must wait for an earlier match of this very step?  Literals are already in place, so only
-                // the destinations [d_j, e_j) of matches j < k matter; they are sorted and disjoint.  a = first j whose
-                // destination ends above my source start (binary search over the lanes by shuffle); my source touches a
-                // destination of the step iff that j lies before me and starts below my source end.  A match that
-                // overlaps its own destination (offset < length) takes the ordered path too.
+                // ---- stage the window: output bytes [d0, d0 + span) as they stand (the literals pass A placed; match bytes are
+                //      still undefined) with aligned 16-byte loads.  Every match of the step writes its bytes to global memory
+                //      AND to the window; a source byte at or above d0 is read from the window.  A chain of matches that feed each
+                //      other then runs at shared-memory latency instead of one L2 round trip per link.
+                const uint32_t gsh = (uint32_t)((uintptr_t)(dst + d0) & 15);
+                {
+                    const uint4* ga = reinterpret_cast<const uint4*>(dst + d0 - gsh);
+                    const uint32_t nvec = (gsh + span + 15) >> 4;
+                    for (uint32_t i = lane; i < nvec; i += 32) reinterpret_cast<uint4*>(S)[i] = ga[i];
+                }
+                const int32_t wb = (int32_t)gsh - (int32_t)d0;          // S[wb + p] = window byte of block position p (p >= d0)
+                __syncwarp();
+                // Which matches must wait for an earlier match of this very step?  Only the destinations [d_j, e_j) of matches
+                // j < k matter (sorted, disjoint): a = first j whose destination ends above my source start (binary search over
+                // the lanes by shuffle); my source touches a destination of the step iff that j lies before me and starts below
+                // my source end.  A match that overlaps its own destination (offset < length) takes the ordered path too.
                 const int32_t e_end = ml ? (int32_t)(d + ml) : 0x7FFFFFFF, d_beg = ml ? (int32_t)d : 0x7FFFFFFF;
                 uint32_t a = 0;
 #pragma unroll
@@ -432,36 +500,41 @@ lz4_exec_blocks_kernel(uint8_t* __restrict__ out, const uint64_t* __restrict__ o
                 }
                 const int32_t da = __shfl_sync(ZMT_FULL_MASK, d_beg, a & 31);
                 const bool indep = ml && off >= ml && !(a < lane && da < sp + (int32_t)ml);
-                if (indep && ml <= LZD_LONG) {
-                    uint8_t* dp = dst + d; const uint8_t* mp = dst + sp;
-                    uint32_t i = 0;
-                    for (; i + 4 <= ml; i += 4) { const uint8_t a = mp[i], b = mp[i + 1], c = mp[i + 2], e = mp[i + 3]; dp[i] = a; dp[i + 1] = b; dp[i + 2] = c; dp[i + 3] = e; }
-                    for (; i < ml; i++) dp[i] = mp[i];
-                }
-                uint32_t lm = __ballot_sync(ZMT_FULL_MASK, indep && ml > LZD_LONG);
-                while (lm) {
-                    const int jl = __ffs(lm) - 1; lm &= lm - 1;
-                    const uint32_t qd = __shfl_sync(ZMT_FULL_MASK, d, jl), qml = __shfl_sync(ZMT_FULL_MASK, ml, jl);
-                    const int32_t qs = __shfl_sync(ZMT_FULL_MASK, sp, jl);
-                    warp_copy_lit(dst + qd, dst + qs, qml, lane);
+                if (indep) {
+                    // own lane: the part of the source below d0 from global memory, the rest (literal bytes of this step) from the window
+                    uint8_t* dp = dst + d; uint8_t* dw = S + (wb + (int32_t)d);
+                    const int32_t nlow = sp >= (int32_t)d0 ? 0 : ((int32_t)d0 - sp < (int32_t)ml ? (int32_t)d0 - sp : (int32_t)ml);
+                    const uint8_t* mp = dst + sp;
+                    int32_t i = 0;
+                    for (; i + 4 <= nlow; i += 4) { const uint8_t x0 = mp[i], x1 = mp[i + 1], x2 = mp[i + 2], x3 = mp[i + 3]; dp[i] = x0; dp[i + 1] = x1; dp[i + 2] = x2; dp[i + 3] = x3; dw[i] = x0; dw[i + 1] = x1; dw[i + 2] = x2; dw[i + 3] = x3; }
+                    for (; i < nlow; i++) { const uint8_t x = mp[i]; dp[i] = x; dw[i] = x; }
+                    for (; i < (int32_t)ml; i++) { const uint8_t x = S[wb + sp + i]; dp[i] = x; dw[i] = x; }
                 }
                 uint32_t dm = __ballot_sync(ZMT_FULL_MASK, ml && !indep);
                 if (dm) __syncwarp();
                 while (dm) {                                            // in order: may read matches of this very step, or themselves
                     const int jq = __ffs(dm) - 1; dm &= dm - 1;
                     const uint32_t qd = __shfl_sync(ZMT_FULL_MASK, d, jq), qml = __shfl_sync(ZMT_FULL_MASK, ml, jq), qoff = __shfl_sync(ZMT_FULL_MASK, off, jq);
-                    uint8_t* dp = dst + qd;
-                    const uint8_t* m = dp - qoff;
-                    if (qoff >= qml) { for (uint32_t i = lane; i < qml; i += 32) dp[i] = m[i]; }
-                    else if (qoff >= 32) { for (uint32_t i = 0; i < qml; i += 32) { if (i + lane < qml) dp[i + lane] = m[i + lane]; __syncwarp(); } }
-                    else { for (uint32_t i = lane; i < qml; i += 32) dp[i] = m[i % qoff]; }
+                    const int32_t qs = (int32_t)qd - (int32_t)qoff;
+                    uint8_t* dp = dst + qd; uint8_t* dw = S + (wb + (int32_t)qd);
+                    if (qoff >= qml) {
+                        for (uint32_t i = lane; i < qml; i += 32) { const int32_t q = qs + (int32_t)i; const uint8_t x = q >= (int32_t)d0 ? S[wb + q] : dst[q]; dp[i] = x; dw[i] = x; }
+                    } else if (qoff >= 32) {                            // overlapping, period >= warp width: 32-byte waves
+                        for (uint32_t i = 0; i < qml; i += 32) {
+                            if (i + lane < qml) { const int32_t q = qs + (int32_t)(i + lane); const uint8_t x = q >= (int32_t)d0 ? S[wb + q] : dst[q]; dp[i + lane] = x; dw[i + lane] = x; }
+                            __syncwarp();
+                        }
+                    } else {                                            // short period: replicate the pattern
+                        for (uint32_t i = lane; i < qml; i += 32) { const int32_t q = qs + (int32_t)(i % qoff); const uint8_t x = q >= (int32_t)d0 ? S[wb + q] : dst[q]; dp[i] = x; dw[i] = x; }
+                    }
                     __syncwarp();
                 }
                 __syncwarp();
-                if (publish && ++since_pub == 4 && base + 32 < B.nrec) {
+                base += nfit;
+                if (publish && ++since_pub == 4 && base < B.nrec) {
                     since_pub = 0;
                     // everything below the first match of the next step is final (literals were placed by pass A)
-                    const uint32_t upto = (uint32_t)R[base + 32] & 0xFFFFFFu;
+                    const uint32_t upto = (uint32_t)R[base] & 0xFFFFFFu;
                     if (lane == 0) { __threadfence(); vprog[t] = upto; }
                 }
             }

@@ -108,6 +108,47 @@ struct BackBits {
     }
 };
 
+// Bit reader for the lane-per-block sequence decoder: one refill per sequence (64 bits ending at the byte that holds the
+// next unread bit: >= 57 valid bits), reads are a shift and a mask.  bitpos = unread bits of the stream; reading below bit 0
+// yields zeros and drives bitpos negative (the caller checks it once per sequence).
+struct FastBits {
+    const uint8_t* p; int32_t bitpos, base, nbytes; uint64_t win;
+    __device__ __forceinline__ bool init(const uint8_t* s, uint32_t n)
+    {
+        nbytes = (int32_t)n; p = s; base = 0; win = 0;
+        if (n == 0) return false;
+        const uint32_t lastb = s[n - 1];
+        if (lastb == 0) return false;
+        bitpos = (int32_t)(n * 8) - (int32_t)(__clz(lastb) - 24 + 1);
+        return true;
+    }
+    __device__ __forceinline__ void refill()
+    {
+        const int32_t tb = bitpos > 0 ? (bitpos + 7) >> 3 : 0;            // bytes [tb - 8, tb) hold the next bits
+        const int32_t b0 = tb - 8;
+        uint64_t w = 0;
+        if (b0 >= 0 && tb + 8 <= nbytes) {
+            const uint8_t* a = p + b0;
+            const uint64_t* A = reinterpret_cast<const uint64_t*>((uintptr_t)a & ~(uintptr_t)7);
+            const uint32_t sh = (uint32_t)((uintptr_t)a & 7) * 8;
+            const uint64_t x = A[0];
+            w = sh ? (x >> sh) | (A[1] << (64 - sh)) : x;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) { const int32_t b = b0 + k; if (b >= 0 && b < nbytes) w |= (uint64_t)p[b] << (8 * k); }
+        }
+        win = w; base = b0 * 8;
+    }
+    // nb <= 32, and at most 57 bits between two refills
+    __device__ __forceinline__ uint32_t read(uint32_t nb)
+    {
+        bitpos -= (int32_t)nb;
+        const int32_t sh = bitpos - base;                                   // >= 0 while the refill discipline holds; negative only past the stream start
+        const uint64_t v = sh >= 0 ? (win >> sh) : (win << (-sh & 63));
+        return (uint32_t)v & (nb >= 32 ? 0xFFFFFFFFu : ((1u << nb) - 1));
+    }
+};
+
 __device__ __forceinline__ void zd_fail(uint32_t* status, uint32_t f, uint32_t code) { atomicCAS(&status[f], 0u, code); }
 
 // literals section header of a compressed block -> header bytes, compressed size, type, size format; false if malformed
@@ -507,16 +548,18 @@ zstd_seq_predef_kernel(const uint8_t* __restrict__ in, const ZBlk* __restrict__ 
     if (nseq == 0) { if (used == qn) { seq_ml[b] = 0; seq_done[b] = 1; } return; }
     if (qn < used + 1 || qp[used] != 0) return;               // not all-predefined: general path
     qp += used + 1; qn -= used + 1;
-    BackBits R;
+    FastBits R;
     if (!R.init(qp, qn)) return;
     ZDSeq* seqs = reinterpret_cast<ZDSeq*>(scratch + B.seq_off);
+    R.refill();
     uint32_t sLL = R.read(6), sOF = R.read(5), sML = R.read(6);
     uint32_t total_ml = 0;
     for (uint32_t i = 0; i < nseq; i++) {
+        R.refill();                                            // >= 57 bits: offset (<= 24) + match extra (<= 16) + literal extra (<= 16)
         const uint32_t eo = pof[sOF], em = pml[sML], el = pll[sLL];
         const uint32_t ofc = eo >> 24, mlc = em >> 24, llc = el >> 24;
-        uint32_t ofv = 1u << ofc;
-        if (ofc > 24) { ofv += R.read(ofc - 16) << 16; ofv += R.read(16); } else ofv += R.read(ofc);
+        if (ofc > 24) return;                                  // windows above 16 MiB: the general path
+        const uint32_t ofv = (1u << ofc) + R.read(ofc);
         const uint32_t mx = mlx[mlc], lx = llx[llc];
         const uint32_t ml = (mx & 0xFFFFFF) + R.read(mx >> 24);
         const uint32_t ll = (lx & 0xFFFFFF) + R.read(lx >> 24);
@@ -525,16 +568,17 @@ zstd_seq_predef_kernel(const uint8_t* __restrict__ in, const ZBlk* __restrict__ 
             return;
         }
         if (i + 1 < nseq) {
+            if (ofc + (mx >> 24) + (lx >> 24) > 40) R.refill();             // rare: keep 17 bits for the three state updates
             sLL = (el & 0xFFFF) + R.read((el >> 16) & 0xFF);
             sML = (em & 0xFFFF) + R.read((em >> 16) & 0xFF);
             sOF = (eo & 0xFFFF) + R.read((eo >> 16) & 0xFF);
         }
-        if (R.off < 0) return;                                 // malformed: the general path redoes the block and reports it
+        if (R.bitpos < 0) return;                              // malformed: the general path redoes the block and reports it
         ZDSeq q; q.ll = ll; q.off = ofv - 3; q.ml = ml; q.pad = 0;
         seqs[i] = q;
         total_ml += ml;
     }
-    if (R.off != 0) return;
+    if (R.bitpos != 0) return;
     seq_ml[b] = total_ml; seq_done[b] = 1;
 }
 
@@ -836,37 +880,58 @@ zstd_entropy_dep_kernel(const uint8_t* __restrict__ in, const ZBlk* __restrict__
     }
 }
 
-// One LANE per frame: the repeat-offset rule (RFC 8878 3.1.1.5) over the frame's sequences in order.  Records written by
-// the block-parallel pass carry the coded offset value and pad = 1.
-__global__ void zstd_resolve_offsets_kernel(const ZBlk* __restrict__ blocks, const uint32_t* __restrict__ frame_first_blk, const uint32_t* __restrict__ frame_seq,
-                                            uint8_t* __restrict__ scratch, uint32_t* __restrict__ status, uint32_t nframes)
+// One WARP per frame: the repeat-offset rule (RFC 8878 3.1.1.5) over the frame's sequences in order.  Records written by the
+// block-parallel pass carry the coded offset value and pad = 1.  32 records are loaded at once (coalesced); the rule itself
+// is a serial state machine over (r0, r1, r2), walked by all lanes in lockstep with the records passed by shuffle; lane j
+// keeps the resolved offset of record j and stores it.
+__global__ void __launch_bounds__(32 * ZD_WARPS)
+zstd_resolve_offsets_kernel(const ZBlk* __restrict__ blocks, const uint32_t* __restrict__ frame_first_blk, const uint32_t* __restrict__ frame_seq,
+                            uint8_t* __restrict__ scratch, uint32_t* __restrict__ status, uint32_t nframes)
 {
-    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t f = blockIdx.x * ZD_WARPS + (threadIdx.x >> 5);
     if (f >= nframes || !(frame_seq[f] & ZF_NEEDS_SEQ) || (status[f] & 0xFF) != 0) return;
     uint32_t r0 = 1, r1 = 4, r2 = 8;
     for (uint32_t b = frame_first_blk[f]; b < frame_first_blk[f + 1]; b++) {
         const ZBlk B = blocks[b];
         if (B.type != ZB_CMP || B.nseq == 0) continue;
         uint4* seqs = reinterpret_cast<uint4*>(scratch + B.seq_off);        // ZDSeq = {ll, off, ml, pad}
-        uint4 nx = seqs[0];
-        for (uint32_t i = 0; i < B.nseq; i++) {
-            const uint4 q = nx;
-            if (i + 1 < B.nseq) nx = seqs[i + 1];                          // next record in flight while this one resolves
-            if (q.w != 1) continue;                                         // not a raw record (block failed): leave it
-            const uint32_t ofv = q.y, ll = q.x;
-            uint32_t off;
-            if (ofv > 3) { off = ofv - 3; r2 = r1; r1 = r0; r0 = off; }
-            else {
-                const uint32_t idx = ofv + (ll == 0 ? 1u : 0u);
-                if (idx == 1) off = r0;
-                else {
-                    off = idx == 4 ? r0 - 1 : (idx == 2 ? r1 : r2);
-                    if (off == 0) { zd_fail(status, f, ZMT_ST_BLOCK); return; }
-                    if (idx > 2) r2 = r1;
-                    r1 = r0; r0 = off;
+        for (uint32_t base = 0; base < B.nseq; base += 32) {
+            const uint32_t cnt = B.nseq - base < 32 ? B.nseq - base : 32;
+            uint4 q = make_uint4(1, 4, 0, 0);
+            if (lane < cnt) q = seqs[base + lane];
+            uint32_t mine = q.y;
+            const uint32_t raw = __ballot_sync(0xFFFFFFFFu, lane < cnt && q.w == 1);
+            if (raw == 0) continue;                                         // block failed or already resolved: leave it
+            const uint32_t reps = __ballot_sync(0xFFFFFFFFu, lane < cnt && q.y <= 3);
+            if (reps == 0) {
+                // no repeat code in these 32: the history is simply the last three offsets
+                mine = q.y - 3;
+                const uint32_t a0 = __shfl_sync(0xFFFFFFFFu, mine, (cnt - 1) & 31);
+                const uint32_t a1 = cnt >= 2 ? __shfl_sync(0xFFFFFFFFu, mine, (cnt - 2) & 31) : r0;
+                const uint32_t a2 = cnt >= 3 ? __shfl_sync(0xFFFFFFFFu, mine, (cnt - 3) & 31) : (cnt == 2 ? r0 : r1);
+                r0 = a0; r1 = a1; r2 = a2;
+            } else {
+                bool bad = false;
+                for (uint32_t j = 0; j < cnt; j++) {
+                    const uint32_t ofv = __shfl_sync(0xFFFFFFFFu, q.y, j), ll = __shfl_sync(0xFFFFFFFFu, q.x, j);
+                    uint32_t off;
+                    if (ofv > 3) { off = ofv - 3; r2 = r1; r1 = r0; r0 = off; }
+                    else {
+                        const uint32_t idx = ofv + (ll == 0 ? 1u : 0u);
+                        if (idx == 1) off = r0;
+                        else {
+                            off = idx == 4 ? r0 - 1 : (idx == 2 ? r1 : r2);
+                            if (off == 0) { bad = true; break; }
+                            if (idx > 2) r2 = r1;
+                            r1 = r0; r0 = off;
+                        }
+                    }
+                    if (lane == j) mine = off;
                 }
+                if (bad) { if (lane == 0) zd_fail(status, f, ZMT_ST_BLOCK); return; }
             }
-            reinterpret_cast<uint32_t*>(seqs + i)[1] = off;
+            if (lane < cnt) { uint32_t* w = reinterpret_cast<uint32_t*>(seqs + base + lane); w[1] = mine; w[3] = 0; }
         }
     }
 }
@@ -993,8 +1058,20 @@ __device__ void zx_block(uint32_t b, uint32_t lane, const uint8_t* __restrict__ 
             // A match whose source ends at or below the step's first output byte reads only finished data and cannot
             // overlap its destination: those run lane-parallel (long ones by the whole warp); the others — reading
             // output of this very step, or themselves — follow in sequence order.
+            // (the destinations [my_mp, my_mp + ml) of a step are sorted and disjoint, its literals are already in place: a match
+            //  is independent iff its source touches no destination of an earlier match of the step — binary search over the
+            //  lanes by shuffle, as in lz4_exec_blocks_kernel — and does not overlap its own destination)
             const bool act = lane < lim && ml != 0;
-            const bool indep = act && (long long)my_mp - (long long)off + (long long)ml <= (long long)op;
+            const long long sp = (long long)my_mp - (long long)off;         // block-relative source start (negative: earlier blocks)
+            const long long e_end = act ? (long long)my_mp + ml : 0x7FFFFFFFFFFFll, d_beg = act ? (long long)my_mp : 0x7FFFFFFFFFFFll;
+            uint32_t a = 0;
+#pragma unroll
+            for (uint32_t stp = 16; stp > 0; stp >>= 1) {
+                const long long v = __shfl_sync(0xFFFFFFFFu, e_end, (a + stp - 1) & 31);
+                if (v <= sp) a += stp;
+            }
+            const long long da = __shfl_sync(0xFFFFFFFFu, d_beg, a & 31);
+            const bool indep = act && off >= ml && !(a < lane && da < sp + (long long)ml);
             if (indep && ml <= 32) {
                 uint8_t* d = dst + my_mp; const uint8_t* m = d - off;
                 uint32_t k = 0;
@@ -1036,17 +1113,62 @@ __device__ void zx_block(uint32_t b, uint32_t lane, const uint8_t* __restrict__ 
     if (lane == 0) { __threadfence(); vdone[b] = 1; }
 }
 
+// Ticket order, as in lz4_exec_blocks_kernel: within a window of ZX_WIN frames block-index-major (block 0 of every frame,
+// then block 1, ...), so that the blocks of one frame — a dependency chain wherever matches reach below their block — are
+// not handed to neighbouring warps, and as many independent chains are in flight as there are frames.  Block (f, b-1)
+// always holds a lower ticket than (f, b).  Windows with very ragged block counts fall back to frame-major order.
+#define ZX_WIN 16384u
+__global__ void __launch_bounds__(256)
+zstd_ticket_windows_kernel(const uint32_t* __restrict__ frame_first_blk, uint32_t nframes, unsigned long long* __restrict__ wbase)
+{
+    __shared__ uint32_t red[256];
+    const uint32_t nwin = (nframes + ZX_WIN - 1) / ZX_WIN;
+    unsigned long long base = 0;
+    for (uint32_t w = 0; w < nwin; w++) {
+        const uint32_t f0 = w * ZX_WIN, f1 = f0 + ZX_WIN < nframes ? f0 + ZX_WIN : nframes;
+        uint32_t mx = 0;
+        for (uint32_t f = f0 + threadIdx.x; f < f1; f += 256) { const uint32_t c = frame_first_blk[f + 1] - frame_first_blk[f]; mx = c > mx ? c : mx; }
+        red[threadIdx.x] = mx;
+        __syncthreads();
+        for (uint32_t d = 128; d > 0; d >>= 1) { if (threadIdx.x < d && red[threadIdx.x + d] > red[threadIdx.x]) red[threadIdx.x] = red[threadIdx.x + d]; __syncthreads(); }
+        mx = red[0];
+        __syncthreads();
+        const unsigned long long real = frame_first_blk[f1] - frame_first_blk[f0], grid = (unsigned long long)(f1 - f0) * mx;
+        const bool frame_major = grid > 8 * real + 65536;
+        if (threadIdx.x == 0) wbase[w] = base | (frame_major ? (1ull << 63) : 0ull);
+        base += frame_major ? real : grid;
+    }
+    if (threadIdx.x == 0) wbase[nwin] = base;
+}
+
 __global__ void __launch_bounds__(32 * ZX_WARPS)
 zstd_execute_kernel(const uint8_t* __restrict__ in, const ZBlk* __restrict__ blocks, uint32_t nblocks, const uint8_t* __restrict__ scratch,
                     const uint32_t* __restrict__ regen, const uint64_t* __restrict__ blk_out, const uint64_t* __restrict__ out_off,
-                    uint8_t* __restrict__ out, uint32_t* __restrict__ done, uint32_t* __restrict__ status, unsigned int* __restrict__ ticket)
+                    uint8_t* __restrict__ out, uint32_t* __restrict__ done, uint32_t* __restrict__ status, unsigned long long* __restrict__ ticket,
+                    const uint32_t* __restrict__ frame_first_blk, const unsigned long long* __restrict__ wbase, uint32_t nframes)
 {
     const uint32_t lane = threadIdx.x & 31;
+    const uint32_t nwin = (nframes + ZX_WIN - 1) / ZX_WIN;
+    const unsigned long long ntickets = wbase[nwin] & ~(1ull << 63);
     for (;;) {
-        uint32_t b = 0;
-        if (lane == 0) b = atomicAdd(ticket, 1u);
-        b = __shfl_sync(0xFFFFFFFFu, b, 0);
-        if (b >= nblocks) return;
+        unsigned long long tk = 0;
+        if (lane == 0) tk = atomicAdd(ticket, 1ull);
+        tk = __shfl_sync(0xFFFFFFFFu, tk, 0);
+        if (tk >= ntickets) return;
+        uint32_t lo = 0, hi = nwin;
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if ((wbase[mid] & ~(1ull << 63)) <= tk) lo = mid; else hi = mid; }
+        const unsigned long long wb = wbase[lo];
+        const unsigned long long tl = tk - (wb & ~(1ull << 63));
+        const uint32_t f0 = lo * ZX_WIN, wn = (f0 + ZX_WIN < nframes ? ZX_WIN : nframes - f0);
+        uint32_t b;
+        if (wb >> 63) b = frame_first_blk[f0] + (uint32_t)tl;
+        else {
+            const uint32_t fb = (uint32_t)(tl / wn), ff = f0 + (uint32_t)(tl % wn);
+            const uint32_t s0 = frame_first_blk[ff];
+            if (fb >= frame_first_blk[ff + 1] - s0) continue;
+            b = s0 + fb;
+        }
+        if (b >= nblocks) continue;
         zx_block(b, lane, in, blocks, scratch, regen, blk_out, out_off, out, done, status);
         __syncwarp();
     }
@@ -1285,7 +1407,7 @@ extern "C" size_t zmt_zstd_blk_desc_bytes(void) { return sizeof(ZBlk); }
 extern "C" size_t zmt_zstdd_workspace_bytes(uint32_t nframes, uint32_t nblocks, uint64_t scratch_bytes)
 {
     return (size_t)(((uint64_t)nblocks * 4 + 255) & ~255ull) * 2 + (((uint64_t)nblocks * 8 + 255) & ~255ull) + (((uint64_t)nframes * 8 + 255) & ~255ull)
-           + 256 + 3 * (size_t)(((uint64_t)nblocks * 4 + 255) & ~255ull) + scratch_bytes + 1024;
+           + 256 + (size_t)((((uint64_t)nframes / ZX_WIN + 2) * 8 + 255) & ~255ull) + 3 * (size_t)(((uint64_t)nblocks * 4 + 255) & ~255ull) + scratch_bytes + 1024;
 }
 
 // d_blocks: nblocks descriptors (device copy of what zmt_zstd_scan_frame_host produced); d_frame_first_blk: nframes+1;
@@ -1302,7 +1424,8 @@ extern "C" int zmt_zstd_decompress_device(const void* d_in, const void* d_blocks
     uint32_t* done = (uint32_t*)w; w += (((uint64_t)nblocks * 4 + 255) & ~255ull);
     uint64_t* blk_out = (uint64_t*)w; w += (((uint64_t)nblocks * 8 + 255) & ~255ull);
     w += (((uint64_t)nframes * 8 + 255) & ~255ull);
-    unsigned int* xticket = (unsigned int*)w; w += 256;
+    unsigned long long* xticket = (unsigned long long*)w; w += 256;
+    unsigned long long* xwbase = (unsigned long long*)w; w += (((uint64_t)nframes / ZX_WIN + 2) * 8 + 255) & ~255ull;
     uint32_t* seq_done = (uint32_t*)w; w += (((uint64_t)nblocks * 4 + 255) & ~255ull);
     uint32_t* seq_ml = (uint32_t*)w; w += (((uint64_t)nblocks * 4 + 255) & ~255ull);
     uint32_t* lit_done = (uint32_t*)w; w += (((uint64_t)nblocks * 4 + 255) & ~255ull);
@@ -1329,7 +1452,7 @@ extern "C" int zmt_zstd_decompress_device(const void* d_in, const void* d_blocks
         if (!no_fast) {
             zstd_entropy_dep_kernel<<<(nblocks + ZD_WARPS - 1) / ZD_WARPS, 32 * ZD_WARPS, 0, stream>>>((const uint8_t*)d_in, (const ZBlk*)d_blocks, nblocks, d_frame_seq, scratch, regen,
                                                                                                d_status, lit_done);
-            zstd_resolve_offsets_kernel<<<(nframes + 63) / 64, 64, 0, stream>>>((const ZBlk*)d_blocks, d_frame_first_blk, d_frame_seq, scratch, d_status, nframes);
+            zstd_resolve_offsets_kernel<<<(nframes + ZD_WARPS - 1) / ZD_WARPS, 32 * ZD_WARPS, 0, stream>>>((const ZBlk*)d_blocks, d_frame_first_blk, d_frame_seq, scratch, d_status, nframes);
         }
         zstd_entropy_seq_kernel<<<(nframes + ZD_WARPS - 1) / ZD_WARPS, 32 * ZD_WARPS, 0, stream>>>((const uint8_t*)d_in, (const ZBlk*)d_blocks, d_frame_first_blk, d_frame_seq,
                                                                                            scratch, regen, d_status, nframes, no_fast ? 0u : 1u);
@@ -1339,9 +1462,10 @@ extern "C" int zmt_zstd_decompress_device(const void* d_in, const void* d_blocks
     if (nblocks) {
         const uint32_t gmax = (uint32_t)(zd_sm_count() * (2048 / (32 * ZX_WARPS)));
         const uint32_t gneed = (nblocks + ZX_WARPS - 1) / ZX_WARPS;
-        cudaMemsetAsync(xticket, 0, 4, stream);
+        cudaMemsetAsync(xticket, 0, 8, stream);
+        zstd_ticket_windows_kernel<<<1, 256, 0, stream>>>(d_frame_first_blk, nframes, xwbase);
         zstd_execute_kernel<<<gneed < gmax ? gneed : gmax, 32 * ZX_WARPS, 0, stream>>>((const uint8_t*)d_in, (const ZBlk*)d_blocks, nblocks, scratch, regen, blk_out,
-                                                                                     d_out_off, (uint8_t*)d_out, done, d_status, xticket);
+                                                                                     d_out_off, (uint8_t*)d_out, done, d_status, xticket, d_frame_first_blk, xwbase, nframes);
         zstd_checksum_kernel<<<(nframes + ZD_WARPS - 1) / ZD_WARPS, 32 * ZD_WARPS, 0, stream>>>((const uint8_t*)d_in, (const ZBlk*)d_blocks, d_frame_first_blk, d_frame_seq,
                                                                                            (const uint8_t*)d_out, d_out_off, (const unsigned long long*)d_out_size, d_status, nframes);
     }
