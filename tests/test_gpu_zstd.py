@@ -218,3 +218,23 @@ def test_zstd_bad_stream_errors(torch):
     assert rc == smax - 5 + 1
     rc, _, _ = z.decompress_mem(z.CODEC_ZSTD, framed[:-50], 2 << 20)  # truncated payload -> data_error (:352-353)
     assert rc == smax - 5 + 1
+
+
+def test_default_chunk_at_level_22_roundtrips(torch):
+    """inputsize = 0 at level 22 means 256 MiB chunks (zstd-mt_compress.c:118-127): one frame larger than every default
+    staging slot — compress and decompress slots must grow (input, output, block table, entropy scratch) instead of failing."""
+    import ctypes
+    M = z.memio_lib()
+    n = (300 << 20) + 1234
+    src = z.gen_stream(z.GEN_TEXT, n, 1 << 20)
+    cap = n + n // 64 + (1 << 20)
+    out = np.empty(cap, np.uint8); st = (ctypes.c_size_t * 5)()
+    rc = M.zmt_zstd_compress_mem(4, 22, 0, src.ctypes.data, n, out.ctypes.data, cap, st)
+    assert rc == 0, z.lib().ZSTDCB_getErrorString(rc)
+    framed = out[: int(st[0])]
+    offs, sizes = z.scan_frames(framed)
+    assert len(offs) == 2 and st[1] == 2                   # 256 MiB + the rest
+    back = np.empty(n + 16, np.uint8)
+    rc = M.zmt_zstd_decompress_mem(4, 0, framed.ctypes.data, framed.size, back.ctypes.data, n + 16, st)
+    assert rc == 0, z.lib().ZSTDCB_getErrorString(rc)
+    assert int(st[0]) == n and np.array_equal(back[:n], src)

@@ -1049,8 +1049,16 @@ extern "C" int zmt_lz4_decompress_device(const void* d_in, uint64_t in_bytes, co
         const uint32_t maxg = (uint32_t)(zmt_sm_count() * 8);
         const uint32_t need = (nslots + LZD_WARPS - 1) / LZD_WARPS;
         ZmtProfScope ps(ZMT_K_LZ4_DEXEC, stream);
-        lz4_exec_blocks_kernel<<<need < maxg ? need : maxg, 32 * LZD_WARPS, 0, stream>>>(
-            (uint8_t*)d_out, d_out_off, d_frame_off, first_slot, tab, rec, prog, d_status, needs_seq, ticket, wbase, nframes, nslots);
+        // measured (profiles/r2_lz4_exec_staged_ab.md): the shared-memory step window wins at every size (4 GiB: 12.2 vs 17.0 ms,
+        // 32 GiB: 53.3 vs 56.7 ms); ZSTDMT_B200_LZ4_STAGED=0 keeps the plain variant for A/B
+        static const char* force = getenv("ZSTDMT_B200_LZ4_STAGED");
+        const bool staged = force ? (*force == '1') : true;
+        if (staged)
+            lz4_exec_blocks_kernel<true><<<need < maxg ? need : maxg, 32 * LZD_WARPS, 0, stream>>>(
+                (uint8_t*)d_out, d_out_off, d_frame_off, first_slot, tab, rec, prog, d_status, needs_seq, ticket, wbase, nframes, nslots);
+        else
+            lz4_exec_blocks_kernel<false><<<need < maxg ? need : maxg, 32 * LZD_WARPS, 0, stream>>>(
+                (uint8_t*)d_out, d_out_off, d_frame_off, first_slot, tab, rec, prog, d_status, needs_seq, ticket, wbase, nframes, nslots);
     }
     zmt_dbg_check(stream, "lz4_exec_blocks_kernel");
     lz4_decode_frames_seq_kernel<<<(nframes + LZD_WARPS - 1) / LZD_WARPS, 32 * LZD_WARPS, 0, stream>>>(

@@ -436,17 +436,20 @@ __device__ uint32_t zd_block(ZWarpTabs& W, const uint8_t* __restrict__ src, uint
                 !zd_seq_table(to, (modes >> 4) & 3, W.of, W.pof, 5, W.norm, qp, qn, 8, 31, hp, &need) ||
                 !zd_seq_table(tm, (modes >> 2) & 3, W.ml, W.pml, 6, W.norm, qp, qn, 9, 52, hp, &need)) { rc = need ? ZD_NEEDS_SEQ : ZMT_ST_BLOCK; break; }
             if (fs) { fs->ll = tl; fs->of = to; fs->ml = tm; fs->have_tabs = true; }
-            BackBits R;
+            FastBits R;                                           // two refills per sequence: <= 31 + 16 bits, then <= 16 + 9 + 9 + 8
             if (!R.init(qp, qn)) { rc = ZMT_ST_BLOCK; break; }
+            R.refill();
             uint32_t sLL = R.read(tl.log), sOF = R.read(to.log), sML = R.read(tm.log);
             uint32_t r0 = fs ? fs->rep[0] : 1, r1 = fs ? fs->rep[1] : 4, r2 = fs ? fs->rep[2] : 8;
             for (uint32_t i = 0; i < nseq; i++) {
+                R.refill();
                 const uint32_t eo = to.t[sOF], em = tm.t[sML], el = tl.t[sLL];
                 const uint32_t ofc = eo >> 24, mlc = em >> 24, llc = el >> 24;
                 if (ofc > 31 || mlc > 52 || llc > 35) { rc = ZMT_ST_BLOCK; break; }
                 uint32_t ofv = 1u << ofc;                         // offset codes above 25 do not occur below 32 MiB windows
                 if (ofc > 24) { ofv += R.read(ofc - 16) << 16; ofv += R.read(16); } else ofv += R.read(ofc);
                 const uint32_t ml = d_ml_base[mlc] + R.read(d_ml_bits[mlc]);
+                R.refill();
                 const uint32_t ll = d_ll_base[llc] + R.read(d_ll_bits[llc]);
                 uint32_t off;
                 if (fs && fs->raw_offsets) off = ofv;             // block-parallel pass: zstd_resolve_offsets_kernel applies the repeat-offset rule
@@ -467,12 +470,12 @@ __device__ uint32_t zd_block(ZWarpTabs& W, const uint8_t* __restrict__ src, uint
                     sML = (em & 0xFFFF) + R.read((em >> 16) & 0xFF);
                     sOF = (eo & 0xFFFF) + R.read((eo >> 16) & 0xFF);
                 }
-                if (R.off < 0) { rc = ZMT_ST_BLOCK; break; }
+                if (R.bitpos < 0) { rc = ZMT_ST_BLOCK; break; }
                 ZDSeq q; q.ll = ll; q.off = off; q.ml = ml; q.pad = (fs && fs->raw_offsets) ? 1u : 0u;
                 seqs[i] = q;
                 total_ml += ml;
             }
-            if (rc == 0 && R.off != 0) rc = ZMT_ST_BLOCK;
+            if (rc == 0 && R.bitpos != 0) rc = ZMT_ST_BLOCK;
             if (rc == 0 && fs) { fs->rep[0] = r0; fs->rep[1] = r1; fs->rep[2] = r2; }
         } while (0);
     }
@@ -989,12 +992,13 @@ __global__ void zstd_offsets_kernel(const ZBlk* __restrict__ blocks, uint32_t nb
 
 // ---------------------------------------------------------------- kernel 3: sequence execution
 #define ZX_WARPS 8
+#define ZX_SPAN 2048u          // bytes a step of the execute pass may regenerate: staged in shared memory
 // One block, one warp.  Blocks are handed out by a ticket counter (see the kernel below), so every block this one may wait
 // for — lower indices of the same frame — is held by a warp that is already running: the wait cannot deadlock whatever
 // order the hardware schedules CTAs in.
 __device__ void zx_block(uint32_t b, uint32_t lane, const uint8_t* __restrict__ in, const ZBlk* __restrict__ blocks, const uint8_t* __restrict__ scratch,
                          const uint32_t* __restrict__ regen, const uint64_t* __restrict__ blk_out, const uint64_t* __restrict__ out_off,
-                         uint8_t* __restrict__ out, uint32_t* __restrict__ done, uint32_t* __restrict__ status)
+                         uint8_t* __restrict__ out, uint32_t* __restrict__ done, uint32_t* __restrict__ status, uint8_t* S)
 {
     const ZBlk B = blocks[b];
     volatile uint32_t* vdone = done;
@@ -1013,30 +1017,72 @@ __device__ void zx_block(uint32_t b, uint32_t lane, const uint8_t* __restrict__ 
         uint32_t waited_to = b;                              // blocks [waited_to, b) are known complete
         const uint64_t blk_abs = blk_out[b];                 // absolute output address of this block
         const uint64_t blk_in_frame = blk_abs - frame_base;
-        // 32 sequences at a time: one coalesced load of the records, positions from two warp scans, every lane copies
-        // its own literal run (literals come from the scratch, not from the output: no ordering among them), then the
-        // matches run in sequence order with the whole warp on each copy.  Per sequence this leaves one dependent
-        // global read (the match source) on the critical path instead of three (record, literals, match).
-        for (uint32_t base = 0; base < B.nseq; base += 32) {
-            const uint32_t cnt = B.nseq - base < 32 ? B.nseq - base : 32;
+        // Up to 32 sequences per step: one coalesced load of the records, positions from two warp scans.  Everything the step
+        // regenerates — at most ZX_SPAN bytes, else the step is cut shorter — is written to global memory AND to a window in
+        // shared memory: every lane copies its own literal run (literals come from the scratch, no ordering among them), then
+        // the matches run; a source byte at or above the step's first output byte is read from the window, so a chain of
+        // matches feeding each other runs at shared-memory latency instead of one L2 round trip per link.
+        for (uint32_t base = 0; base < B.nseq;) {
+            uint32_t cnt = B.nseq - base < 32 ? B.nseq - base : 32;
             uint32_t ll = 0, off = 0, ml = 0;
             if (lane < cnt) { const ZDSeq q = seqs[base + lane]; ll = q.ll; off = q.off; ml = q.ml; }
             uint32_t it = ll + ml, il = ll;                  // inclusive scans: output bytes, literal bytes
+            if (lane < cnt && (ll > rg || ml > rg)) { it = 0x40000000u; }    // absurd lengths: caught below, keep the scan from wrapping
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, it, d), c = __shfl_up_sync(0xFFFFFFFFu, il, d);
-                if (lane >= (uint32_t)d) { it += a; il += c; }
+                if (lane >= (uint32_t)d) { it = (it + a) | ((it | a) & 0x40000000u); il += c; }
             }
+            const uint32_t nfit = __popc(__ballot_sync(0xFFFFFFFFu, lane < cnt && it <= ZX_SPAN));      // sorted: a prefix
+            if (nfit == 0) {
+                // the first sequence alone is larger than the window: straight in global memory, by the whole warp
+                const uint32_t qll = __shfl_sync(0xFFFFFFFFu, ll, 0), qoff = __shfl_sync(0xFFFFFFFFu, off, 0), qml = __shfl_sync(0xFFFFFFFFu, ml, 0);
+                const uint32_t mp = op + qll;
+                if ((uint64_t)op + qll + qml > rg || (uint64_t)lp + qll > B.regen_hint || qoff == 0 || (uint64_t)qoff > blk_in_frame + mp) { bad = true; break; }
+                for (uint32_t k = lane; k < qll; k += 32) dst[op + k] = lit[lp + k];
+                if (qoff > mp) {
+                    const unsigned long long need = blk_abs + mp - qoff;
+                    bool waited = false;
+                    while (waited_to > 0 && blocks[waited_to - 1].frame == B.frame && blk_out[waited_to - 1] + regen[waited_to - 1] > need) {
+                        waited_to--; waited = true;
+                        if (lane == 0) { while (vdone[waited_to] == 0) __nanosleep(64); }
+                    }
+                    __syncwarp();
+                    if (waited) __threadfence();
+                }
+                __syncwarp();
+                uint8_t* d = dst + mp;
+                const uint8_t* m = d - qoff;
+                if (qoff >= qml) { for (uint32_t k = lane; k < qml; k += 32) d[k] = m[k]; }
+                else if (qoff >= 32) { for (uint32_t k = 0; k < qml; k += 32) { if (k + lane < qml) d[k + lane] = m[k + lane]; __syncwarp(); } }
+                else { for (uint32_t k = lane; k < qml; k += 32) d[k] = m[k % qoff]; }
+                __syncwarp();
+                op += qll + qml; lp += qll; base += 1;
+                continue;
+            }
+            cnt = nfit;
+            if (lane >= cnt) { ll = 0; ml = 0; }
             const uint32_t my_op = op + it - (ll + ml), my_lp = lp + il - ll, my_mp = my_op + ll;
             const bool mybad = lane < cnt && ((uint64_t)my_op + ll + ml > rg || (uint64_t)my_lp + ll > B.regen_hint || off == 0 || (uint64_t)off > blk_in_frame + my_mp);
             const uint32_t badmask = __ballot_sync(0xFFFFFFFFu, mybad);
-            const uint32_t lim = badmask ? (uint32_t)(__ffs(badmask) - 1) : cnt;      // sequences of this batch that are executed
-            if (lane < lim && ll <= 32) { for (uint32_t k = 0; k < ll; k++) dst[my_op + k] = lit[my_lp + k]; }
+            const uint32_t lim = badmask ? (uint32_t)(__ffs(badmask) - 1) : cnt;      // sequences of this step that are executed
+            const int32_t wb = -(int32_t)op;                                           // S[wb + p] = window byte of block position p (op <= p < op + ZX_SPAN)
+            if (lane < lim && ll <= 32) {
+                // loads first, stores after, 8 bytes at a time: a byte-wise load -> store loop pays one L2 latency per byte
+                const uint8_t* ls = lit + my_lp; uint8_t* d = dst + my_op; uint8_t* dw = S + (wb + (int32_t)my_op);
+                for (uint32_t k = 0; k < ll; k += 8) {
+                    uint8_t x[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) x[j] = (k + j < ll) ? ls[k + j] : (uint8_t)0;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) if (k + j < ll) { d[k + j] = x[j]; dw[k + j] = x[j]; }
+                }
+            }
             uint32_t longmask = __ballot_sync(0xFFFFFFFFu, lane < lim && ll > 32);
             while (longmask) {                                // long literal runs: the whole warp copies
                 const int jl = __ffs(longmask) - 1; longmask &= longmask - 1;
                 const uint32_t o = __shfl_sync(0xFFFFFFFFu, my_op, jl), l0 = __shfl_sync(0xFFFFFFFFu, my_lp, jl), n = __shfl_sync(0xFFFFFFFFu, ll, jl);
-                for (uint32_t k = lane; k < n; k += 32) dst[o + k] = lit[l0 + k];
+                for (uint32_t k = lane; k < n; k += 32) { const uint8_t x = lit[l0 + k]; dst[o + k] = x; S[wb + (int32_t)(o + k)] = x; }
             }
             // ---- matches.  Any source below this block: wait (once per step) for the earlier blocks it touches.
             {
@@ -1054,53 +1100,57 @@ __device__ void zx_block(uint32_t b, uint32_t lane, const uint8_t* __restrict__ 
                     if (waited) __threadfence();
                 }
             }
-            __syncwarp();                                                   // this step's literals are in place
-            // A match whose source ends at or below the step's first output byte reads only finished data and cannot
-            // overlap its destination: those run lane-parallel (long ones by the whole warp); the others — reading
-            // output of this very step, or themselves — follow in sequence order.
-            // (the destinations [my_mp, my_mp + ml) of a step are sorted and disjoint, its literals are already in place: a match
-            //  is independent iff its source touches no destination of an earlier match of the step — binary search over the
-            //  lanes by shuffle, as in lz4_exec_blocks_kernel — and does not overlap its own destination)
+            __syncwarp();                                                   // this step's literals are in place (global and window)
+            // (the destinations [my_mp, my_mp + ml) of a step are sorted and disjoint: a match is independent iff its source
+            //  touches no destination of an earlier match of the step — binary search over the lanes by shuffle, as in
+            //  lz4_exec_blocks_kernel — and does not overlap its own destination; independent matches run lane-parallel)
             const bool act = lane < lim && ml != 0;
-            const long long sp = (long long)my_mp - (long long)off;         // block-relative source start (negative: earlier blocks)
-            const long long e_end = act ? (long long)my_mp + ml : 0x7FFFFFFFFFFFll, d_beg = act ? (long long)my_mp : 0x7FFFFFFFFFFFll;
+            const int32_t sp = (int32_t)my_mp - (int32_t)off;               // block-relative source start (negative: earlier blocks)
+            const int32_t e_end = act ? (int32_t)(my_mp + ml) : 0x7FFFFFFF, d_beg = act ? (int32_t)my_mp : 0x7FFFFFFF;
             uint32_t a = 0;
 #pragma unroll
             for (uint32_t stp = 16; stp > 0; stp >>= 1) {
-                const long long v = __shfl_sync(0xFFFFFFFFu, e_end, (a + stp - 1) & 31);
+                const int32_t v = __shfl_sync(0xFFFFFFFFu, e_end, (a + stp - 1) & 31);
                 if (v <= sp) a += stp;
             }
-            const long long da = __shfl_sync(0xFFFFFFFFu, d_beg, a & 31);
-            const bool indep = act && off >= ml && !(a < lane && da < sp + (long long)ml);
+            const int32_t da = __shfl_sync(0xFFFFFFFFu, d_beg, a & 31);
+            const bool indep = act && off >= ml && !(a < lane && da < sp + (int32_t)ml);
             if (indep && ml <= 32) {
-                uint8_t* d = dst + my_mp; const uint8_t* m = d - off;
-                uint32_t k = 0;
-                for (; k + 4 <= ml; k += 4) { const uint8_t a0 = m[k], a1 = m[k + 1], a2 = m[k + 2], a3 = m[k + 3]; d[k] = a0; d[k + 1] = a1; d[k + 2] = a2; d[k + 3] = a3; }
-                for (; k < ml; k++) d[k] = m[k];
+                uint8_t* d = dst + my_mp; uint8_t* dw = S + (wb + (int32_t)my_mp);
+                const int32_t nlow = sp >= (int32_t)op ? 0 : ((int32_t)op - sp < (int32_t)ml ? (int32_t)op - sp : (int32_t)ml);
+                const uint8_t* m = dst + sp;
+                int32_t k = 0;
+                for (; k < nlow; k += 8) {
+                    uint8_t x[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) x[j] = (k + j < nlow) ? m[k + j] : (uint8_t)0;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) if (k + j < nlow) { d[k + j] = x[j]; dw[k + j] = x[j]; }
+                }
+                k = nlow;
+                for (; k < (int32_t)ml; k++) { const uint8_t x = S[wb + sp + k]; d[k] = x; dw[k] = x; }
             }
-            uint32_t lm = __ballot_sync(0xFFFFFFFFu, indep && ml > 32);
-            while (lm) {
-                const int jl = __ffs(lm) - 1; lm &= lm - 1;
-                const uint32_t qoff = __shfl_sync(0xFFFFFFFFu, off, jl), qml = __shfl_sync(0xFFFFFFFFu, ml, jl), mp = __shfl_sync(0xFFFFFFFFu, my_mp, jl);
-                uint8_t* d = dst + mp; const uint8_t* m = d - qoff;
-                for (uint32_t k = lane; k < qml; k += 32) d[k] = m[k];
-            }
-            uint32_t dm = __ballot_sync(0xFFFFFFFFu, act && !indep);
+            uint32_t dm = __ballot_sync(0xFFFFFFFFu, act && !(indep && ml <= 32));       // long independent ones and the dependent ones: in order, whole warp
             if (dm) __syncwarp();
             while (dm) {
                 const int jq = __ffs(dm) - 1; dm &= dm - 1;
                 const uint32_t qoff = __shfl_sync(0xFFFFFFFFu, off, jq), qml = __shfl_sync(0xFFFFFFFFu, ml, jq), mp = __shfl_sync(0xFFFFFFFFu, my_mp, jq);
-                uint8_t* d = dst + mp;
-                const uint8_t* m = d - qoff;
-                if (qoff >= qml) { for (uint32_t k = lane; k < qml; k += 32) d[k] = m[k]; }
-                else if (qoff >= 32) { for (uint32_t k = 0; k < qml; k += 32) { if (k + lane < qml) d[k + lane] = m[k + lane]; __syncwarp(); } }
-                else { for (uint32_t k = lane; k < qml; k += 32) d[k] = m[k % qoff]; }
+                const int32_t qs = (int32_t)mp - (int32_t)qoff;
+                uint8_t* d = dst + mp; uint8_t* dw = S + (wb + (int32_t)mp);
+                if (qoff >= qml) { for (uint32_t k = lane; k < qml; k += 32) { const int32_t q = qs + (int32_t)k; const uint8_t x = q >= (int32_t)op ? S[wb + q] : dst[q]; d[k] = x; dw[k] = x; } }
+                else if (qoff >= 32) {
+                    for (uint32_t k = 0; k < qml; k += 32) {
+                        if (k + lane < qml) { const int32_t q = qs + (int32_t)(k + lane); const uint8_t x = q >= (int32_t)op ? S[wb + q] : dst[q]; d[k + lane] = x; dw[k + lane] = x; }
+                        __syncwarp();
+                    }
+                } else { for (uint32_t k = lane; k < qml; k += 32) { const int32_t q = qs + (int32_t)(k % qoff); const uint8_t x = q >= (int32_t)op ? S[wb + q] : dst[q]; d[k] = x; dw[k] = x; } }
                 __syncwarp();
             }
             __syncwarp();
             if (badmask) { bad = true; break; }
             op += __shfl_sync(0xFFFFFFFFu, it, cnt - 1);
             lp += __shfl_sync(0xFFFFFFFFu, il, cnt - 1);
+            base += cnt;
         }
         if (!bad) {
             const uint32_t rest = B.regen_hint - lp;
@@ -1147,6 +1197,7 @@ zstd_execute_kernel(const uint8_t* __restrict__ in, const ZBlk* __restrict__ blo
                     uint8_t* __restrict__ out, uint32_t* __restrict__ done, uint32_t* __restrict__ status, unsigned long long* __restrict__ ticket,
                     const uint32_t* __restrict__ frame_first_blk, const unsigned long long* __restrict__ wbase, uint32_t nframes)
 {
+    __shared__ __align__(16) uint8_t stage[ZX_WARPS][ZX_SPAN];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t nwin = (nframes + ZX_WIN - 1) / ZX_WIN;
     const unsigned long long ntickets = wbase[nwin] & ~(1ull << 63);
@@ -1169,7 +1220,7 @@ zstd_execute_kernel(const uint8_t* __restrict__ in, const ZBlk* __restrict__ blo
             b = s0 + fb;
         }
         if (b >= nblocks) continue;
-        zx_block(b, lane, in, blocks, scratch, regen, blk_out, out_off, out, done, status);
+        zx_block(b, lane, in, blocks, scratch, regen, blk_out, out_off, out, done, status, stage[threadIdx.x >> 5]);
         __syncwarp();
     }
 }
