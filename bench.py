@@ -701,6 +701,8 @@ def run_b200(args):
             except AssertionError:
                 raise
             except Exception as e:
+                if job.world > 1:
+                    raise                                   # a rank that skips the rest of a leg would leave the others in its collectives
                 extra[name] = {"error": repr(e)}
     line["extra"] = extra
     if job.rank == 0:

@@ -85,3 +85,24 @@ def test_explicit_device_list(ngpu):
     after = batches(ngpu)
     assert rc == 0 and np.array_equal(out, o.orc_encode_lz4(src, chunk))
     assert after[1] > before[1] and after[0] == before[0]
+
+
+def test_calling_thread_gets_its_cuda_device_back(ngpu):
+    """The pipeline switches the calling thread between the GPUs it deals to; on return the thread's current device must be
+    the one it came with (a CUDA / torch caller keeps its own notion of it).  Checked at the driver level."""
+    import ctypes
+    import torch
+    cu = ctypes.CDLL("libcuda.so.1")
+    def cur():
+        d = ctypes.c_int(-1)
+        assert cu.cuCtxGetDevice(ctypes.byref(d)) == 0
+        return d.value
+    torch.cuda.set_device(0)
+    torch.zeros(1, device="cuda")                       # make device 0's context current on this thread
+    assert cur() == 0
+    src = z.gen_stream(z.GEN_TEXT, 64 << 20, 1 << 20)
+    rc, framed, _ = with_gpus("all", lambda: z.compress_mem(z.CODEC_LZ4, src, threads=4, level=1, chunk=1 << 20))
+    assert rc == 0 and cur() == 0
+    rc, back, _ = with_gpus("all", lambda: z.decompress_mem(z.CODEC_LZ4, framed, src.size + 16, threads=4))
+    assert rc == 0 and cur() == 0 and np.array_equal(back, src)
+    assert float(torch.ones(4, device="cuda").sum().item()) == 4.0 and torch.cuda.current_device() == 0

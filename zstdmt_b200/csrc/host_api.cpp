@@ -176,6 +176,14 @@ CpuSet common_local_cpus(const std::vector<int>& devs)
     return r;
 }
 
+// The pipeline switches the calling thread's current CUDA device while it deals batches over ZSTDMT_GPUS; a drop-in
+// library must hand the thread back as it found it (a torch / CUDA caller keeps its own notion of the current device).
+struct DeviceRestore {
+    int prev = -1;
+    DeviceRestore() { if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; } }
+    ~DeviceRestore() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 // ------------------------------------------------------------------ optional stage timing (ZSTDMT_B200_TRACE=1)
 struct StageClock {
     double cb = 0, wait = 0, gpu = 0;       // seconds: inside callbacks / waiting for a slot or queue / CUDA sync + copies
@@ -344,6 +352,7 @@ void ctx_release_slots(Ctx* c) { for (auto& s : c->pipe.slots) if (s.ok) slot_fr
 // ------------------------------------------------------------------ compression
 size_t compress_run(Ctx* c, GenRdWr* rw)
 {
+    const DeviceRestore restore_device;
     const ErrCodes& E = *c->E;
     const CodecOps* ops = codec_ops(c->codec);
     if (!ops->compress || !ops->c_work || !ops->c_bound) { c->lib_errcode = ZMT_ST_UNSUPPORTED; return E.library; }
@@ -695,6 +704,7 @@ size_t decompress_single_stream(Ctx* c, GenRdWr* rw, const uint8_t* first, size_
 
 size_t decompress_run(Ctx* c, GenRdWr* rw)
 {
+    const DeviceRestore restore_device;
     const ErrCodes& E = *c->E;
     Pipe& P = c->pipe;
     const bool is_zstd = c->codec == CODEC_ZSTD;
@@ -999,7 +1009,7 @@ Ctx* ctx_new(int codec, bool comp, int threads, int level, size_t inputsize)
     c->E = codec == CODEC_LZ4 ? &kErrLz4 : &kErrZstd;
     return c;
 }
-void ctx_delete(Ctx* c) { if (!c) return; ctx_release_slots(c); delete c; }
+void ctx_delete(Ctx* c) { if (!c) return; const DeviceRestore restore_device; ctx_release_slots(c); delete c; }
 
 // Levels.  The device encoders implement one search class per codec (LZ4: the greedy single-probe parse of level 1-2;
 // zstd: the same parse + Huffman / predefined-FSE entropy stage, "level 3 (predefined FSE tables)" in BASELINE terms).

@@ -30,7 +30,8 @@
 #define LZD_WARPS 8
 #define LZD_WIN   512u        // compressed bytes staged per step and warp (one 16-byte load per lane)
 #define LZD_NJ    256u        // token-start candidates examined per step
-#define LZD_LONG  32u         // literal runs / matches longer than this are copied by the whole warp
+#define LZD_LONG  32u         // matches longer than this are copied by the whole warp
+#define LZD_LONGLIT 16u       // literal runs longer than this are copied by the whole warp (pass A: few lanes hold long runs)
 #define LZD_ERR   0xFFFFFFFFu
 #define LZD_DONE  0xFFFFFFFFu // progress value of a finished block
 
@@ -225,15 +226,18 @@ __device__ uint32_t lzd_parse_block(uint8_t* win, uint8_t* J, const uint8_t* gsr
         {
             const uint32_t base = sh + 8 * lane;
             const uint32_t w0 = lds32u(win, base), w1 = lds32u(win, base + 4);
+            // the "next token in front of the block end" test only matters in the last stretch of a block
+            const bool near_end = ip0 + LZD_NJ + 24 >= srcSize;
             uint32_t j0 = 0, j1 = 0;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const uint32_t tok = ((j < 4 ? w0 : w1) >> (8 * (j & 3))) & 0xFF;
                 const uint32_t lit = tok >> 4;
-                uint32_t d = 3 + lit;
-                bool fast = lit != 15;
-                if ((tok & 15) == 15) { fast = fast && win[base + j + d] != 255; d++; }      // lit < 15: index <= 15 + 255 + 18 < LZD_WIN
-                fast = fast && ip0 + 8 * lane + j + d < srcSize;
+                const uint32_t m15 = (tok & 15) == 15 ? 1u : 0u;
+                const uint32_t ext = win[base + j + 3 + lit];                          // the byte a one-byte match-length extension would be (index < 290)
+                const uint32_t d = 3 + lit + m15;
+                bool fast = lit != 15 && !(m15 && ext == 255);
+                if (near_end) fast = fast && ip0 + 8 * lane + j + d < srcSize;
                 const uint32_t v = fast ? d : 0;
                 if (j < 4) j0 |= v << (8 * j); else j1 |= v << (8 * (j - 4));
             }
@@ -283,7 +287,7 @@ __device__ uint32_t lzd_parse_block(uint8_t* win, uint8_t* J, const uint8_t* gsr
         bad = bad || (lane < cnt && ((uint64_t)my_op + tot > dcap || (s.ml && (s.off == 0 || (uint64_t)s.off > (uint64_t)my_mp + hist))));
         if (__any_sync(ZMT_FULL_MASK, bad)) return LZD_ERR;
         // ---- literals: own run per lane, long runs by the whole warp
-        if (s.lit && s.lit <= LZD_LONG) {
+        if (s.lit && s.lit <= LZD_LONGLIT) {
             uint8_t* d = dst + my_op;
             const uint32_t r = s.litpos - (uint32_t)W.pos;
             const uint8_t* sp = (r + s.lit <= LZD_WIN) ? win + r : gsrc + s.litpos;      // generic pointer: shared or global
@@ -291,7 +295,7 @@ __device__ uint32_t lzd_parse_block(uint8_t* win, uint8_t* J, const uint8_t* gsr
             for (; i + 4 <= s.lit; i += 4) { const uint8_t a = sp[i], b = sp[i + 1], c = sp[i + 2], e = sp[i + 3]; d[i] = a; d[i + 1] = b; d[i + 2] = c; d[i + 3] = e; }
             for (; i < s.lit; i++) d[i] = sp[i];
         }
-        uint32_t longmask = __ballot_sync(ZMT_FULL_MASK, s.lit > LZD_LONG);
+        uint32_t longmask = __ballot_sync(ZMT_FULL_MASK, s.lit > LZD_LONGLIT);
         while (longmask) {
             const int jl = __ffs(longmask) - 1; longmask &= longmask - 1;
             const uint32_t o = __shfl_sync(ZMT_FULL_MASK, my_op, jl), lp = __shfl_sync(ZMT_FULL_MASK, s.litpos, jl), n = __shfl_sync(ZMT_FULL_MASK, s.lit, jl);

@@ -436,20 +436,17 @@ __device__ uint32_t zd_block(ZWarpTabs& W, const uint8_t* __restrict__ src, uint
                 !zd_seq_table(to, (modes >> 4) & 3, W.of, W.pof, 5, W.norm, qp, qn, 8, 31, hp, &need) ||
                 !zd_seq_table(tm, (modes >> 2) & 3, W.ml, W.pml, 6, W.norm, qp, qn, 9, 52, hp, &need)) { rc = need ? ZD_NEEDS_SEQ : ZMT_ST_BLOCK; break; }
             if (fs) { fs->ll = tl; fs->of = to; fs->ml = tm; fs->have_tabs = true; }
-            FastBits R;                                           // two refills per sequence: <= 31 + 16 bits, then <= 16 + 9 + 9 + 8
-            if (!R.init(qp, qn)) { rc = ZMT_ST_BLOCK; break; }
-            R.refill();
+            BackBits R;                                           // (the one-refill-per-sequence reader of the lane-per-block kernel needs two
+            if (!R.init(qp, qn)) { rc = ZMT_ST_BLOCK; break; }    //  refills here — described tables, offsets to 31 bits — and measured slower: 6.9 -> 8.5 ms)
             uint32_t sLL = R.read(tl.log), sOF = R.read(to.log), sML = R.read(tm.log);
             uint32_t r0 = fs ? fs->rep[0] : 1, r1 = fs ? fs->rep[1] : 4, r2 = fs ? fs->rep[2] : 8;
             for (uint32_t i = 0; i < nseq; i++) {
-                R.refill();
                 const uint32_t eo = to.t[sOF], em = tm.t[sML], el = tl.t[sLL];
                 const uint32_t ofc = eo >> 24, mlc = em >> 24, llc = el >> 24;
                 if (ofc > 31 || mlc > 52 || llc > 35) { rc = ZMT_ST_BLOCK; break; }
                 uint32_t ofv = 1u << ofc;                         // offset codes above 25 do not occur below 32 MiB windows
                 if (ofc > 24) { ofv += R.read(ofc - 16) << 16; ofv += R.read(16); } else ofv += R.read(ofc);
                 const uint32_t ml = d_ml_base[mlc] + R.read(d_ml_bits[mlc]);
-                R.refill();
                 const uint32_t ll = d_ll_base[llc] + R.read(d_ll_bits[llc]);
                 uint32_t off;
                 if (fs && fs->raw_offsets) off = ofv;             // block-parallel pass: zstd_resolve_offsets_kernel applies the repeat-offset rule
@@ -470,12 +467,12 @@ __device__ uint32_t zd_block(ZWarpTabs& W, const uint8_t* __restrict__ src, uint
                     sML = (em & 0xFFFF) + R.read((em >> 16) & 0xFF);
                     sOF = (eo & 0xFFFF) + R.read((eo >> 16) & 0xFF);
                 }
-                if (R.bitpos < 0) { rc = ZMT_ST_BLOCK; break; }
+                if (R.off < 0) { rc = ZMT_ST_BLOCK; break; }
                 ZDSeq q; q.ll = ll; q.off = off; q.ml = ml; q.pad = (fs && fs->raw_offsets) ? 1u : 0u;
                 seqs[i] = q;
                 total_ml += ml;
             }
-            if (rc == 0 && R.bitpos != 0) rc = ZMT_ST_BLOCK;
+            if (rc == 0 && R.off != 0) rc = ZMT_ST_BLOCK;
             if (rc == 0 && fs) { fs->rep[0] = r0; fs->rep[1] = r1; fs->rep[2] = r2; }
         } while (0);
     }
