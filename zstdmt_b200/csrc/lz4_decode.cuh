@@ -438,10 +438,12 @@ lz4_exec_blocks_kernel(uint8_t* __restrict__ out, const uint64_t* __restrict__ o
             bool prev_done = !linked;
             uint32_t since_pub = 0;
             uint8_t* const S = stage[STAGED ? (threadIdx.x >> 5) : 0];
+            // The records of the NEXT step are loaded while this one executes (one L2 round trip less on the chain of a block).
+            unsigned long long rnext = lane < B.nrec ? R[lane] : 0ull;
             for (uint32_t base = 0; base < B.nrec;) {
                 const uint32_t cnt = B.nrec - base < 32 ? B.nrec - base : 32;
                 uint32_t d = 0, ml = 0, off = 0;
-                if (lane < cnt) { const unsigned long long r = R[base + lane]; d = (uint32_t)r & 0xFFFFFFu; ml = (uint32_t)(r >> 24) & 0xFFFFFFu; off = (uint32_t)(r >> 48); }
+                { const unsigned long long r = lane < cnt ? rnext : 0ull; d = (uint32_t)r & 0xFFFFFFu; ml = (uint32_t)(r >> 24) & 0xFFFFFFu; off = (uint32_t)(r >> 48); }
                 const uint32_t d0 = __shfl_sync(ZMT_FULL_MASK, d, 0);
                 // ---- the step = the longest prefix of these records whose destinations fit the staging window [d0, d0 + LZX_SPAN)
                 const uint32_t nfit = STAGED ? __popc(__ballot_sync(ZMT_FULL_MASK, ml && d + ml - d0 <= LZX_SPAN)) : cnt;       // destinations are sorted: a prefix
@@ -464,8 +466,10 @@ lz4_exec_blocks_kernel(uint8_t* __restrict__ out, const uint64_t* __restrict__ o
                     else { for (uint32_t i = lane; i < qml; i += 32) dp[i] = m[i % qoff]; }
                     __syncwarp();
                     base += 1;
+                    rnext = base + lane < B.nrec ? R[base + lane] : 0ull;
                     continue;
                 }
+                rnext = base + nfit + lane < B.nrec ? R[base + nfit + lane] : 0ull;      // in flight until the next step reads it
                 if (lane >= nfit) ml = 0;
                 const uint32_t span = __shfl_sync(ZMT_FULL_MASK, d + ml, nfit - 1) - d0;
                 const int32_t sp = (int32_t)d - (int32_t)off;           // block-relative source; negative = previous block
@@ -483,18 +487,6 @@ lz4_exec_blocks_kernel(uint8_t* __restrict__ out, const uint64_t* __restrict__ o
                         if (pv == LZD_DONE) prev_done = true;
                     }
                 }
-                // ---- stage the window: output bytes [d0, d0 + span) as they stand (the literals pass A placed; match bytes are
-                //      still undefined) with aligned 16-byte loads.  Every match of the step writes its bytes to global memory
-                //      AND to the window; a source byte at or above d0 is read from the window.  A chain of matches that feed each
-                //      other then runs at shared-memory latency instead of one L2 round trip per link.
-                const uint32_t gsh = (uint32_t)((uintptr_t)(dst + d0) & 15);
-                if (STAGED) {
-                    const uint4* ga = reinterpret_cast<const uint4*>(dst + d0 - gsh);
-                    const uint32_t nvec = (gsh + span + 15) >> 4;
-                    for (uint32_t i = lane; i < nvec; i += 32) reinterpret_cast<uint4*>(S)[i] = ga[i];
-                }
-                const int32_t wb = (int32_t)gsh - (int32_t)d0;          // S[wb + p] = window byte of block position p (p >= d0)
-                __syncwarp();
                 // Which matches must wait for an earlier match of this very step?  Only the destinations [d_j, e_j) of matches
                 // j < k matter (sorted, disjoint): a = first j whose destination ends above my source start (binary search over
                 // the lanes by shuffle); my source touches a destination of the step iff that j lies before me and starts below
@@ -508,12 +500,31 @@ lz4_exec_blocks_kernel(uint8_t* __restrict__ out, const uint64_t* __restrict__ o
                 }
                 const int32_t da = __shfl_sync(ZMT_FULL_MASK, d_beg, a & 31);
                 const bool indep = ml && off >= ml && !(a < lane && da < sp + (int32_t)ml);
-                if (indep && ml <= LZD_LONG) {
-                    // own lane: the part of the source below d0 from global memory, the rest (literal bytes of this step) from the window
+                const bool own = indep && ml <= LZD_LONG;               // copied by its own lane
+                // own lane: the part of the source below d0 comes from global memory — its first 8 bytes are requested NOW, before
+                // the window load below stalls on its own round trip (one latency per step instead of two)
+                const int32_t nlow = !own ? 0 : !STAGED ? (int32_t)ml : sp >= (int32_t)d0 ? 0 : ((int32_t)d0 - sp < (int32_t)ml ? (int32_t)d0 - sp : (int32_t)ml);
+                const uint8_t* mp = dst + sp;
+                uint8_t x0[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) x0[j] = (j < nlow) ? mp[j] : (uint8_t)0;
+                // ---- stage the window: output bytes [d0, d0 + span) as they stand (the literals pass A placed; match bytes are
+                //      still undefined) with aligned 16-byte loads.  Every match of the step writes its bytes to global memory
+                //      AND to the window; a source byte at or above d0 is read from the window.  A chain of matches that feed each
+                //      other then runs at shared-memory latency instead of one L2 round trip per link.
+                const uint32_t gsh = (uint32_t)((uintptr_t)(dst + d0) & 15);
+                if (STAGED) {
+                    const uint4* ga = reinterpret_cast<const uint4*>(dst + d0 - gsh);
+                    const uint32_t nvec = (gsh + span + 15) >> 4;
+                    for (uint32_t i = lane; i < nvec; i += 32) reinterpret_cast<uint4*>(S)[i] = ga[i];
+                }
+                const int32_t wb = (int32_t)gsh - (int32_t)d0;          // S[wb + p] = window byte of block position p (p >= d0)
+                __syncwarp();
+                if (own) {
                     uint8_t* dp = dst + d; uint8_t* dw = S + (wb + (int32_t)d);
-                    const int32_t nlow = !STAGED ? (int32_t)ml : sp >= (int32_t)d0 ? 0 : ((int32_t)d0 - sp < (int32_t)ml ? (int32_t)d0 - sp : (int32_t)ml);
-                    const uint8_t* mp = dst + sp;
-                    int32_t i = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) if (j < nlow) { dp[j] = x0[j]; if (STAGED) dw[j] = x0[j]; }
+                    int32_t i = 8;
                     for (; i < nlow; i += 8) {                              // loads first, stores after: one L2 latency per 8 bytes, not per byte
                         uint8_t x[8];
 #pragma unroll
@@ -524,7 +535,7 @@ lz4_exec_blocks_kernel(uint8_t* __restrict__ out, const uint64_t* __restrict__ o
                     i = nlow;
                     for (; i < (int32_t)ml; i++) { const uint8_t x = S[wb + sp + i]; dp[i] = x; dw[i] = x; }        // STAGED only (nlow == ml otherwise)
                 }
-                uint32_t dm = __ballot_sync(ZMT_FULL_MASK, ml && !(indep && ml <= LZD_LONG));      // long independent ones too: whole warp
+                uint32_t dm = __ballot_sync(ZMT_FULL_MASK, ml && !own);      // long independent ones too: whole warp
                 if (dm) __syncwarp();
                 while (dm) {                                            // in order: may read matches of this very step, or themselves
                     const int jq = __ffs(dm) - 1; dm &= dm - 1;
