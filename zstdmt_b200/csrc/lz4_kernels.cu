@@ -866,6 +866,26 @@ static inline int zmt_sm_count()
     return n[dev];
 }
 
+// side stream + fork / join events, one set per (device, host thread): a set must not be shared by two launch sequences
+// that interleave, and every host thread enqueues its own sequences in order
+struct ZmtSide { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, join = nullptr; bool ok = false; };
+static ZmtSide zmt_side_stream()
+{
+    static const bool off = getenv("ZSTDMT_B200_NO_SIDE_STREAM") != nullptr;
+    thread_local ZmtSide side[64];
+    int dev = 0;
+    if (off || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return ZmtSide();
+    ZmtSide& s = side[dev];
+    if (!s.ok && !s.stream) {
+        bool ok = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) cudaGetLastError();
+        s.ok = ok;
+    }
+    return s;
+}
+
 extern "C" uint32_t zmt_chunk_count(uint64_t in_bytes, uint32_t chunk_size)
 {
     if (chunk_size == 0) return 0;
@@ -918,6 +938,8 @@ extern "C" int zmt_lz4_compress_device(const void* d_in, uint64_t in_bytes, uint
         cudaFuncSetAttribute(lz77_blocks_kernel<0, LZ4_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     }
     static const bool no_pipe = getenv("ZSTDMT_B200_NOPIPE") != nullptr;   // A/B knob: single-team schedule (same output bytes)
+    const ZmtSide side = zmt_side_stream();
+    if (side.ok) cudaEventRecord(side.fork, stream);
     { ZmtProfScope ps(ZMT_K_LZ4_COMPRESS, stream);
     if (no_pipe || smem_bytes != sizeof(CompressSmem))
         lz77_blocks_kernel<0, LZ4_NT><<<gridc, LZ4_NT, smem_bytes, stream>>>((const uint8_t*)d_in, in_bytes, chunk_size, d_chunk_bytes, bpc, tmp, blk_csize, nblocks, getenv("ZSTDMT_B200_NO_TMA") ? 1u : 0u, nullptr);
@@ -932,8 +954,19 @@ extern "C" int zmt_lz4_compress_device(const void* d_in, uint64_t in_bytes, uint
         lz4_blocks_pipe_kernel<<<gridc, 2 * P_TEAM, sizeof(PipeSmem), stream>>>((const uint8_t*)d_in, in_bytes, chunk_size, d_chunk_bytes, bpc, tmp, blk_csize, nblocks, getenv("ZSTDMT_B200_NO_TMA") ? 1u : 0u);
     } }
     zmt_dbg_check(stream, "lz4 block compressor");
-    { ZmtProfScope ps(ZMT_K_XXH32, stream);
-    xxh32_kernel<<<(nchunks + X_WARPS - 1) / X_WARPS, 32 * X_WARPS, 0, stream>>>((const uint8_t*)d_in, nullptr, nullptr, d_chunk_bytes, chunk_size, in_bytes, chk, nchunks); }
+    // The content checksum only reads the input.  It cannot share an SM with the compressor (two compressor CTAs hold every
+    // register of an SM), but enqueued on a side stream BEHIND the compressor's launch it fills the SMs the compressor's last,
+    // ragged wave leaves idle, instead of starting when the last CTA has retired; the pack kernel joins both.
+    if (side.ok) {
+        cudaStreamWaitEvent(side.stream, side.fork, 0);          // fork = everything before the compressor launch (the input is ready)
+        { ZmtProfScope ps(ZMT_K_XXH32, side.stream);
+        xxh32_kernel<<<(nchunks + X_WARPS - 1) / X_WARPS, 32 * X_WARPS, 0, side.stream>>>((const uint8_t*)d_in, nullptr, nullptr, d_chunk_bytes, chunk_size, in_bytes, chk, nchunks); }
+        cudaEventRecord(side.join, side.stream);
+        cudaStreamWaitEvent(stream, side.join, 0);
+    } else {
+        ZmtProfScope ps(ZMT_K_XXH32, stream);
+        xxh32_kernel<<<(nchunks + X_WARPS - 1) / X_WARPS, 32 * X_WARPS, 0, stream>>>((const uint8_t*)d_in, nullptr, nullptr, d_chunk_bytes, chunk_size, in_bytes, chk, nchunks);
+    }
     zmt_dbg_check(stream, "xxh32_kernel");
     { ZmtProfScope ps(ZMT_K_LZ4_SIZES, stream);
     lz4_frame_sizes_kernel<<<(nchunks + 255) / 256, 256, 0, stream>>>(blk_csize, in_bytes, chunk_size, d_chunk_bytes, bpc, nchunks, frame_size); }
