@@ -1,0 +1,3 @@
+set -x
+cd $GRAFT_REPO_ROOT
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29631 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/r2_bench_n2.json 2> gpurun_out/r2_bench_n2.err; tail -c 600 gpurun_out/r2_bench_n2.err; grep "^{" gpurun_out/r2_bench_n2.json | cut -c1-300

@@ -210,7 +210,7 @@ const CodecOps* codec_ops(int codec)
 struct Slot {
     int dev = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev = nullptr;
+    cudaEvent_t ev = nullptr, evp[2] = { nullptr, nullptr };       // evp: decompress writer, output pieces in flight
     uint8_t *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr, *d_work = nullptr;
     size_t in_cap = 0, out_cap = 0, work_cap = 0, tab_cap = 0;   // tab_cap: entries in the tables below
     // tables: pinned host mirror + device copy, one allocation each
@@ -252,6 +252,7 @@ void slot_free_raw(Slot& s)
     if (s.h_blk) cudaFreeHost(s.h_blk);
     if (s.d_blk) cudaFree(s.d_blk);
     if (s.ev) cudaEventDestroy(s.ev);
+    for (int k = 0; k < 2; k++) if (s.evp[k]) cudaEventDestroy(s.evp[k]);
     if (s.stream) cudaStreamDestroy(s.stream);
     s = Slot();
 }
@@ -264,6 +265,7 @@ bool slot_alloc_raw(Slot& s, int dev, size_t in_cap, size_t out_cap, size_t work
     bool ok = true;
     ok = ok && cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming) == cudaSuccess;
+    for (int k = 0; k < 2; k++) ok = ok && cudaEventCreateWithFlags(&s.evp[k], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaHostAlloc((void**)&s.h_in, in_cap + 64, cudaHostAllocPortable) == cudaSuccess;
     ok = ok && cudaHostAlloc((void**)&s.h_out, out_cap + 64, cudaHostAllocPortable) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&s.d_in, in_cap + 256) == cudaSuccess;
@@ -714,6 +716,7 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
     const uint32_t kBlkCap = 32768;
     // decode batches must hold enough frames to fill the GPU (one warp per 64 KiB block): 32 MiB of frames measured best
     const size_t in_cap0 = (env_size("ZSTDMT_B200_DBATCH_MB", 32) << 20), out_cap0 = in_cap0 * 2, tab_cap = 8192;
+    const uint64_t piece_bytes = (uint64_t)env_size("ZSTDMT_B200_D2H_PIECE_MB", 2) << 20;      // 0: whole slot right after the kernels (measured 0 / 2 / 4 / 8 MiB: 12.8 / 15.1 / 14.3 / 12.8 GB/s)
 
     // ---- stream-type sniffing on the calling thread (LZ4MT_decompressDCtx, lz4-mt_decompress.c:503-520;
     //      ZSTDCB_decompressDCtx, zstd-mt_decompress.c:721-759)
@@ -945,12 +948,35 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
             if (tr) wr_clk.gpu += StageClock::now() - tg0;
             Tables T = tables_at(s->h_tab, s->tab_cap);
             bool bad = false;
+            // The decoded bytes come over in pieces of a few MiB, one piece ahead of the one being written: what fn_write's
+            // memcpy reads was DMA-written moments ago and is still in the last-level cache, instead of a whole 64 MiB slot that
+            // was copied long before its first byte is used.
+            uint32_t issued = 0, ready = 0; int np_issued = 0, np_ready = 0;       // frames [0, issued) requested, [0, ready) landed
+            auto issue_piece = [&]() -> bool {
+                if (issued >= s->n) return true;
+                uint32_t j = issued; uint64_t lo = T.b[j], hi = lo;
+                while (j < s->n && hi - lo < piece_bytes) { hi = T.b[j] + T.c[j]; j++; }
+                if (hi > s->out_cap) hi = s->out_cap;
+                if (hi > lo && cudaMemcpyAsync(s->h_out + lo, s->d_out + lo, (size_t)(hi - lo), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess) return false;
+                if (cudaEventRecord(s->evp[np_issued & 1], s->stream) != cudaSuccess) return false;
+                np_issued++; issued = j;
+                return true;
+            };
+            uint32_t piece_end[2] = { 0, 0 };
             for (uint32_t i = 0; i < s->n; i++) {
                 const uint32_t st = T.e[i];
                 if (st != ZMT_ST_OK) {
                     c->lib_errcode = st;
                     P.fail((st == ZMT_ST_TRUNCATED || st == ZMT_ST_TRAILING) ? E.frame_decompress : E.library);
                     bad = true; break;
+                }
+                if (piece_bytes && i >= ready) {
+                    bool okp = true;
+                    if (np_issued == np_ready) { okp = issue_piece(); piece_end[(np_issued - 1) & 1] = issued; }
+                    if (okp && issued < s->n && np_issued == np_ready + 1) { okp = issue_piece(); piece_end[(np_issued - 1) & 1] = issued; }   // one ahead
+                    if (okp) okp = cudaEventSynchronize(s->evp[np_ready & 1]) == cudaSuccess;
+                    if (!okp) { c->lib_errcode = ZMT_ST_CUDA; P.fail(E.library); bad = true; break; }
+                    ready = piece_end[np_ready & 1]; np_ready++;
                 }
                 GenBuffer b; b.buf = s->h_out + T.b[i]; b.size = (size_t)T.c[i]; b.allocated = b.size;
                 const double tc0 = tr ? StageClock::now() : 0;
@@ -984,7 +1010,7 @@ size_t decompress_run(Ctx* c, GenRdWr* rw)
                                             : zmt_lz4_decompress_device(s->d_in, s->in_used, Td.a, Td.d, s->n, s->nslots, s->d_out, Td.b, Td.c, Td.e, s->d_work, s->stream);
         if (s->dev >= 0 && s->dev < 64) g_dev_batches[s->dev]++;
         if (st == ZMT_ST_OK) {
-            if (s->out_used) ce = cudaMemcpyAsync(s->h_out, s->d_out, s->out_used, cudaMemcpyDeviceToHost, s->stream);
+            if (s->out_used && piece_bytes == 0) ce = cudaMemcpyAsync(s->h_out, s->d_out, s->out_used, cudaMemcpyDeviceToHost, s->stream);
             if (ce == cudaSuccess) ce = cudaMemcpyAsync(Th.c, Td.c, (size_t)s->n * 8, cudaMemcpyDeviceToHost, s->stream);
             if (ce == cudaSuccess) ce = cudaMemcpyAsync(Th.e, Td.e, (size_t)s->n * 4, cudaMemcpyDeviceToHost, s->stream);
             if (ce == cudaSuccess) ce = cudaEventRecord(s->ev, s->stream);
