@@ -1,5 +1,5 @@
 // lz4_kernels.cu — hand-written sm_100a kernels: the LZ77 front end shared by both codecs, the LZ4 back end
-// (block format, XXH32, frame pack, decoder) and the launchers of the Zstandard encoder (entropy stage in
+// (block format, XXH32, frame pack; the decoder is in lz4_decode.cuh) and the launchers of the Zstandard encoder (entropy stage in
 // zstd_entropy.cuh; the Zstandard decoder lives in zstd_decode.cu).
 //
 // Replaces the arithmetic the reference reaches through
@@ -15,7 +15,8 @@
 //   lz4_frame_sizes_kernel / lz4_frame_pack_kernel
 //                               frame size per chunk -> exclusive scan -> compaction of the block
 //                               payloads + LZ4F header/end-mark/checksum + skippable header.
-//   lz4_decode_frames_kernel    one warp per frame, warp-lockstep sequence decode.
+//   lz4_decode.cuh              the LZ4F decoder: frame scan, pass A (token parse + literals + match records), pass B (match
+//                               execution by ticket, step window in SMEM), sequential fallback for partial-block frames.
 //
 // The compressor's match/parse rule is deterministic and restated on the CPU in
 // oracle/lz4_oracle.c:orc_lz4_block_compress_b200 (tests compare bit-exact).

@@ -1,23 +1,31 @@
 // zstd_decode.cu — Zstandard frame decoding on sm_100a (the ZSTD_decompressStream step of
 // /root/reference/lib/zstd-mt_decompress.c:442-527, one frame per 12-byte container header).
 //
-// Three kernels per batch, all block-parallel (a zstd frame of a 1 MiB chunk has ~64 blocks):
-//   zstd_entropy_kernel   one warp per block (self-contained blocks: what our encoder emits): literals (raw / RLE /
-//                         Huffman, lanes 0..3 own the streams) and sequences (lane 0 walks the FSE states) are decoded
-//                         into per-block scratch; the block's regenerated size = literals + sum of match lengths
-//   zstd_entropy_seq_kernel  one warp per FRAME for frames whose blocks depend on earlier ones (treeless literals,
-//                         Repeat_Mode tables, repeat offsets — what libzstd emits for the reference): same routine,
-//                         blocks in order, state carried
-//   zstd_offsets_kernel   one thread per frame: exclusive scan of the regenerated sizes -> output offset per block,
-//                         content-size check against the frame header
-//   zstd_execute_kernel   one warp per block: literal / match copies in sequence order; a match that reaches below
-//                         the block's own output waits for the `done` flags of the blocks it reads from
-// Host side (zmt_zstd_scan_host): walks frame + block headers (3 bytes per block) and sizes the scratch.
+// Kernels per batch, all block-parallel (a zstd frame of a 1 MiB chunk has ~64 blocks of ours, 8 of libzstd's):
+//   zstd_seq_predef_kernel   one LANE per block: the sequences of blocks on the predefined FSE tables (everything our encoder
+//                            writes) — 32 serial state chains per warp instruction
+//   zstd_literals_kernel     8 blocks per warp: lane 4g + j decodes Huffman stream j of block g (table per group in SMEM; weights
+//                            direct or FSE-coded; treeless literals take the tree from the block the host scan named)
+//   zstd_entropy_kernel      one warp per block: whatever the two above left (raw / RLE literals, described tables)
+//   zstd_entropy_dep_kernel  one warp per block of a frame with inter-block state (treeless literals, Repeat_Mode tables, repeat
+//                            offsets — what libzstd emits for the reference): inherited tables are rebuilt from the describing
+//                            block's header, offsets stay as coded; zstd_resolve_offsets_kernel (one warp per frame) then
+//                            applies the repeat-offset rule over the frame's records in order
+//   zstd_entropy_seq_kernel  one warp per FRAME, blocks in order, state carried: only frames a block-parallel decoder flags at
+//                            run time (a repeat offset where the headers showed no state)
+//   zstd_offsets_kernel      one thread per frame: exclusive scan of the regenerated sizes -> output offset per block,
+//                            content-size check against the frame header
+//   zstd_execute_kernel      one warp per block, blocks by ticket (block-index-major): up to 32 sequences per step, written to
+//                            global memory and to a window in SMEM; a match that reaches below the block's own output waits for
+//                            the `done` flags of the blocks it reads from
+//   zstd_checksum_kernel     one warp per frame with a content checksum: XXH64 of the regenerated frame
+// Host side (zmt_zstd_scan_frame_host): walks frame + block headers (3 bytes per block + the two section headers), sizes the
+// scratch, names per block the block whose header describes each table it uses, flags per frame (state, checksum, no size).
 //
 // Scope: the full block format of RFC 8878 — raw / RLE / compressed blocks, Huffman literals with direct
 // or FSE-coded weights, 1 or 4 streams, treeless reuse, sequence tables predefined / RLE / FSE-described / repeat,
-// repeat offsets — i.e. what libzstd emits for the reference.  Not handled (reported per frame
-// as ZMT_ST_UNSUPPORTED, never decoded on the CPU): dictionaries, frames without a content size, XXH64 checksums.
+// repeat offsets, content checksum, frames without a content size — i.e. what libzstd and the zstd CLI emit (SURVEY.md
+// fact 0.6).  Not handled (reported per frame as ZMT_ST_UNSUPPORTED, never decoded on the CPU): dictionaries.
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
