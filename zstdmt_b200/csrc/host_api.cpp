@@ -361,11 +361,11 @@ size_t compress_run(Ctx* c, GenRdWr* rw)
     Pipe& P = c->pipe;
     const size_t chunk = c->inputsize;
     // Slots in flight: the call is bound by the serialised callbacks (one memcpy stream); a GPU turns a batch around in a
-    // fraction of the time the reader needs to fill the next one, so more devices do not need more slots per device — one
-    // each is enough — and the whole ring should stay inside the last-level cache, which is what the callbacks' memcpy runs
-    // against (measured on the 2-socket Xeon hosts of the B200 pool: 4 slots x 8 MiB 17.4 GB/s, 8 x 8 MiB 14.0, 4 x 4 MiB 15.8,
-    // 4 x 16 MiB 14.4).  So: slots = max(2..4 by `threads`, devices), batch = 32 MiB / slots (2..8 MiB) unless
-    // ZSTDMT_B200_BATCH_MB / ZSTDMT_B200_SLOTS say otherwise.
+    // fraction of the time the reader needs to fill the next one, so more devices do not need more slots per device — one each
+    // is enough.  Measured on the 2-socket Xeon hosts of the B200 pool (one GPU, 4 GiB, GB/s end to end): 4 slots x 8 MiB 18.2
+    // (the default), 4 x 4 MiB 15.8, 4 x 16 MiB 14.4, 8 x 8 MiB 13.7, 8 x 4 MiB 9.9, 16 x 2 MiB 5.2: a ring that outgrows the
+    // last-level cache slows the callbacks' memcpy, and small batches pay the per-batch launch + copy latency.  A call over 8
+    // devices therefore runs 8 x 8 MiB (14.3 GB/s): sharing a 4-slot host ring between 8 device-side slots is the open lead.
     if (P.slots.empty()) {
         c->devs = env_devices();
         if (c->devs.empty()) { c->lib_errcode = ZMT_ST_CUDA; return E.library; }
@@ -373,8 +373,7 @@ size_t compress_run(Ctx* c, GenRdWr* rw)
     const size_t base_slots = c->threads >= 4 ? 4 : c->threads >= 3 ? 3 : 2;
     size_t nsl = env_size("ZSTDMT_B200_SLOTS", base_slots > c->devs.size() ? base_slots : c->devs.size());
     if (nsl < 2) nsl = 2; if (nsl < c->devs.size()) nsl = c->devs.size(); if (nsl > 64) nsl = 64;
-    size_t dflt_mb = 32 / nsl; if (dflt_mb < 2) dflt_mb = 2; if (dflt_mb > 8) dflt_mb = 8;
-    size_t batch_bytes = env_size("ZSTDMT_B200_BATCH_MB", dflt_mb) << 20;
+    size_t batch_bytes = env_size("ZSTDMT_B200_BATCH_MB", 8) << 20;
     size_t B = batch_bytes / chunk; if (B < 1) B = 1; if (B > 65536) B = 65536;
 
     if (P.slots.empty()) {
