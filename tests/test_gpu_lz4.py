@@ -251,3 +251,22 @@ def test_python_callbacks_observe_reference_call_pattern(torch):
     assert L.LZ4MT_GetInsizeCCtx(ctx) == n and L.LZ4MT_GetOutsizeCCtx(ctx) == sum(map(len, writes))
     L.LZ4MT_freeCCtx(ctx)
     assert b"".join(writes) == o.orc_encode_lz4(src, chunk).tobytes()
+
+
+@pytest.mark.parametrize("spec", ["0,0,0,0,0,0", "0,0,0,0,0,0,0,0"])
+def test_more_device_slots_than_host_buffers_share_the_pinned_ring(torch, spec, monkeypatch):
+    """A call over more devices than it keeps batches in flight: the device-side slots beyond the fourth borrow the pinned
+    staging buffers of slot i % 4 and the reader holds batch q + 4 back until batch q is written.  One GPU named several times
+    stands in for several GPUs; the stream must be byte-identical, the counters too."""
+    monkeypatch.setenv("ZSTDMT_GPUS", spec)
+    n, chunk = (150 << 20) + 4321, 1 << 20
+    src = z.gen_stream(z.GEN_MIX, n, chunk)
+    rc, framed, st = z.compress_mem(z.CODEC_LZ4, src, threads=4, level=1, chunk=chunk)
+    assert rc == 0 and st["frames"] == -(-n // chunk) and st["insize"] == n and st["outsize"] == framed.size
+    assert np.array_equal(framed, o.orc_encode_lz4(src, chunk))
+    rc, zf, zst = z.compress_mem(z.CODEC_ZSTD, src[: 40 << 20], threads=4, level=3, chunk=chunk)
+    assert rc == 0
+    rc, back, _ = z.decompress_mem(z.CODEC_ZSTD, zf, (40 << 20) + 16, threads=4)
+    assert rc == 0 and np.array_equal(back, src[: 40 << 20])
+    rc, back, _ = z.decompress_mem(z.CODEC_LZ4, framed, n + 16, threads=4)
+    assert rc == 0 and np.array_equal(back, src)

@@ -224,6 +224,7 @@ struct Slot {
     size_t in_used = 0, out_used = 0;
     int state = 0;               // 0 free, 1 filled, 2 submitted
     bool ok = false;
+    bool host_alias = false;     // h_in / h_out are borrowed from another slot of the same context (never pooled, never freed here)
 };
 
 // table layout (entries = tab_cap):  u64 a[cap+1] | u64 b[cap+1] | u64 c[cap+1] | u64 f[cap+1] | u32 d[cap] | u32 e[cap] | u32 g[cap+1]
@@ -292,7 +293,7 @@ bool slot_alloc(Slot& s, int dev, size_t in_cap, size_t out_cap, size_t work_cap
         std::lock_guard<std::mutex> g(g_pool_mu);
         for (size_t i = 0; i < g_pool.size(); i++) {
             Slot& c = g_pool[i];
-            if (c.dev == dev && c.in_cap >= in_cap && c.out_cap >= out_cap && c.work_cap >= work_cap && c.tab_cap == tab_cap) {
+            if (c.h_in && c.dev == dev && c.in_cap >= in_cap && c.out_cap >= out_cap && c.work_cap >= work_cap && c.tab_cap == tab_cap) {
                 s = c; g_pool.erase(g_pool.begin() + (long)i);
                 s.state = 0; s.n = 0; s.in_used = s.out_used = 0;
                 return true;
@@ -302,8 +303,53 @@ bool slot_alloc(Slot& s, int dev, size_t in_cap, size_t out_cap, size_t work_cap
     return slot_alloc_raw(s, dev, in_cap, out_cap, work_cap, tab_cap);
 }
 
+// A slot whose pinned staging buffers are those of `owner` (a call over more devices than it keeps batches in flight: the
+// host ring stays 4 x 8 MiB — cache-resident for the callbacks' memcpy — while every device has its own device-side buffers).
+bool slot_alloc_alias(Slot& s, const Slot& owner, int dev, size_t in_cap, size_t out_cap, size_t work_cap, size_t tab_cap)
+{
+    {
+        std::lock_guard<std::mutex> g(g_pool_mu);                       // a pooled device-only slot of a previous call
+        for (size_t i = 0; i < g_pool.size(); i++) {
+            Slot& c = g_pool[i];
+            if (!c.h_in && c.dev == dev && c.in_cap >= in_cap && c.out_cap >= out_cap && c.work_cap >= work_cap && c.tab_cap == tab_cap) {
+                s = c; g_pool.erase(g_pool.begin() + (long)i);
+                s.state = 0; s.n = 0; s.in_used = s.out_used = 0;
+                s.h_in = owner.h_in; s.h_out = owner.h_out; s.host_alias = true;
+                return true;
+            }
+        }
+    }
+    s.dev = dev;
+    if (cudaSetDevice(dev) != cudaSuccess) return false;
+    bool ok = true;
+    ok = ok && cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming) == cudaSuccess;
+    for (int k = 0; k < 2; k++) ok = ok && cudaEventCreateWithFlags(&s.evp[k], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&s.d_in, in_cap + 256) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&s.d_out, out_cap + 256) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&s.d_work, work_cap + 256) == cudaSuccess;
+    s.tab_bytes = tables_bytes(tab_cap);
+    ok = ok && cudaHostAlloc((void**)&s.h_tab, s.tab_bytes, cudaHostAllocPortable) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&s.d_tab, s.tab_bytes) == cudaSuccess;
+    s.in_cap = in_cap; s.out_cap = out_cap; s.work_cap = work_cap; s.tab_cap = tab_cap; s.ok = ok;
+    if (!ok) { cudaGetLastError(); slot_free_raw(s); return false; }
+    s.h_in = owner.h_in; s.h_out = owner.h_out; s.host_alias = true;
+    return true;
+}
+
 void slot_free(Slot& s)
 {
+    if (s.host_alias) {
+        // hand the borrowed buffers back (they belong to the owner slot); the device side goes to the pool as a device-only slot
+        s.h_in = nullptr; s.h_out = nullptr; s.host_alias = false;
+        if (s.ok) {
+            cudaSetDevice(s.dev);
+            if (s.stream) cudaStreamSynchronize(s.stream);
+            std::lock_guard<std::mutex> g(g_pool_mu);
+            if (g_pool.size() < kPoolMax && !getenv("ZSTDMT_B200_NO_POOL")) { g_pool.push_back(s); s = Slot(); return; }
+        }
+        slot_free_raw(s); return;
+    }
     if (s.ok) {
         cudaSetDevice(s.dev);
         if (s.stream) cudaStreamSynchronize(s.stream);
@@ -349,7 +395,12 @@ struct Ctx {
     const ErrCodes* E = nullptr;
 };
 
-void ctx_release_slots(Ctx* c) { for (auto& s : c->pipe.slots) if (s.ok) slot_free(s); c->pipe.slots.clear(); }
+void ctx_release_slots(Ctx* c)
+{
+    for (auto& s : c->pipe.slots) if (s.ok && s.host_alias) slot_free(s);         // borrowers before the owners of the host buffers
+    for (auto& s : c->pipe.slots) if (s.ok) slot_free(s);
+    c->pipe.slots.clear();
+}
 
 // ------------------------------------------------------------------ compression
 size_t compress_run(Ctx* c, GenRdWr* rw)
@@ -374,16 +425,23 @@ size_t compress_run(Ctx* c, GenRdWr* rw)
     size_t nsl = env_size("ZSTDMT_B200_SLOTS", base_slots > c->devs.size() ? base_slots : c->devs.size());
     if (nsl < 2) nsl = 2; if (nsl < c->devs.size()) nsl = c->devs.size(); if (nsl > 64) nsl = 64;
     size_t batch_bytes = env_size("ZSTDMT_B200_BATCH_MB", 8) << 20;
+    const bool no_alias = getenv("ZSTDMT_B200_NO_RING_SHARE") != nullptr;          // A/B knob: every slot its own pinned buffers
+    if (!no_alias && nsl > base_slots) nsl = (nsl + base_slots - 1) / base_slots * base_slots;   // batch q uses host buffer q % base_slots: needs base_slots | slots
     size_t B = batch_bytes / chunk; if (B < 1) B = 1; if (B > 65536) B = 65536;
 
     if (P.slots.empty()) {
         P.slots.resize(nsl);
         for (size_t i = 0; i < P.slots.size(); i++) {
-            if (!slot_alloc(P.slots[i], c->devs[i % c->devs.size()], B * chunk, (size_t)ops->c_bound((uint32_t)B, (uint32_t)chunk),
-                            ops->c_work((uint32_t)B, (uint32_t)chunk), B)) { ctx_release_slots(c); return E.mem; }
+            const size_t ic = B * chunk, oc = (size_t)ops->c_bound((uint32_t)B, (uint32_t)chunk), wc = ops->c_work((uint32_t)B, (uint32_t)chunk);
+            const bool okk = (i < base_slots || no_alias) ? slot_alloc(P.slots[i], c->devs[i % c->devs.size()], ic, oc, wc, B)
+                                                          : slot_alloc_alias(P.slots[i], P.slots[i % base_slots], c->devs[i % c->devs.size()], ic, oc, wc, B);
+            if (!okk) { ctx_release_slots(c); return E.mem; }
         }
     }
     const size_t N = P.slots.size();
+    // batches in flight: slots beyond the first `base_slots` borrow their pinned buffers from slot i % base_slots, so batch q + H
+    // may only be filled once batch q has been written
+    const size_t H = (N > base_slots && !no_alias) ? base_slots : N;
     P.fill_seq = P.submit_seq = P.write_seq = 0; P.reader_done = false; P.error = 0;
     for (auto& s : P.slots) s.state = 0;
 
@@ -399,7 +457,7 @@ size_t compress_run(Ctx* c, GenRdWr* rw)
                 const double t0 = StageClock::now();
                 std::unique_lock<std::mutex> lk(P.mu);
                 s = &P.slots[P.fill_seq % N];
-                P.cv.wait(lk, [&] { return s->state == 0 || P.error; });
+                P.cv.wait(lk, [&] { return (s->state == 0 && P.fill_seq - P.write_seq < H) || P.error; });
                 ck_r.wait += StageClock::now() - t0;
                 if (P.error) break;
             }
